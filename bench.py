@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the ProtoASNet prototype-head hot path on B200 (contract: see DESIGN.md 'Measurement').
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one prototype-head forward (BASELINE config 3: feature map 512x4x7x7 bf16, D=256, P=40, K=4) over a
+batch of 1024 synthetic clips per GPU.  ``value`` = clips/s with the feature maps resident in HBM; ``e2e`` = the same
+through the public module API with pinned HOST buffers (H2D of the batch + D2H of logits/similarity inside the timed
+region); ``push`` = seconds for one push / prototype projection over 50 000 clips sharded across the N ranks
+(fused similarity+argmin, one NCCL all-reduce(MIN) of packed keys + one all-reduce(SUM) of winner rows).
+``--impl reference`` times the reference algorithm's CPU port (oracle/, op-for-op the reference's PyTorch ops) on
+the host cores of the box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "cfg3_video_b1024"
+BATCH = 1024
+PUSH_CLIPS = 50000
+
+
+def flops_bytes_per_clip(d):
+    C, D, P, K, S = d.C, d.D, d.P, d.K, d.S
+    addon = 2 * C * D * S + 2 * D * D * S
+    occ = 2 * C * D * S + 2 * D * (D // 2) * S + 2 * (D // 2) * P * S
+    pool = 2 * P * D * S
+    tail = 6 * P * D + 2 * P * K
+    nbytes = C * S * 2 + P * S * 2 + (P + K) * 4
+    return addon + occ + pool + tail, nbytes
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load" = samples in the upper half of what we saw
+        load = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_model(dims, device, path):
+    import protoasnet_b200 as pasn
+    from protoasnet_b200 import synth, _lib
+
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    m = pasn.construct_Video_XProtoNet(pasn.FeatureInput(dims.C), pretrained=False, prototype_shape=dims.prototype_shape,
+                                       num_classes=dims.K)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(device).eval()
+    m.kernel_path = {"auto": _lib.PASN_PATH_AUTO, "generic": _lib.PASN_PATH_GENERIC, "tcgen05": _lib.PASN_PATH_TCGEN05}[path]
+    return m, sd
+
+
+def cpu_port_clips_per_sec(dims, sd, clips_per_run, min_seconds, max_runs, threads):
+    """The reference's head on the host CPU (oracle port: the same PyTorch ops the reference executes), fp32, no_grad,
+    in chunks of 64 clips (batch 1024 would allocate 8 GB for the reference's broadcast product)."""
+    from oracle import head_oracle as ho
+    from protoasnet_b200 import synth
+
+    torch.set_num_threads(threads)
+    tsd = ho.to_torch_sd(sd)
+    x = torch.from_numpy(synth.make_features(dims, min(64, clips_per_run), seed=0, bf16_round=True))
+    chunks = max(1, clips_per_run // x.shape[0])
+    with torch.no_grad():
+        ho.head_forward_torch(x, tsd)  # warm-up
+        times = []
+        t_all = time.perf_counter()
+        while len(times) < max_runs and (len(times) < 3 or time.perf_counter() - t_all < min_seconds):
+            t0 = time.perf_counter()
+            for _ in range(chunks):
+                ho.head_forward_torch(x, tsd)
+            times.append(time.perf_counter() - t0)
+    return chunks * x.shape[0] / float(np.median(times)), chunks * x.shape[0], len(times)
+
+
+def run_reference(args, rank):
+    from protoasnet_b200 import synth
+
+    if rank != 0:
+        return
+    dims = synth.CONFIGS[WORKLOAD]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    from oracle import head_oracle as ho
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tsd = ho.to_torch_sd(sd)
+    sample = 128
+    x = torch.from_numpy(synth.make_features(dims, 64, seed=0, bf16_round=True))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            ho.head_forward_torch(x, tsd)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for _ in range(sample // 64):
+                ho.head_forward_torch(x, tsd)
+        dt = time.perf_counter() - t0
+    v = args.steps * sample / dt
+    desc = f"{sample} clips per step (2 chunks of 64) of the cfg-3 batch-1024 workload, fp32, torch CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "head_fwd_clips_per_sec", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: prototype head fwd, feature map 512x4x7x7, D=256 P=40 K=4", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "tcgen05"])
+    ap.add_argument("--push-clips", type=int, default=PUSH_CLIPS)
+    ap.add_argument("--no-push", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from protoasnet_b200 import _lib, synth
+    from protoasnet_b200.push import push_resident
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _lib.load()
+    dims = synth.CONFIGS[WORKLOAD]
+    model, sd = make_model(dims, dev, args.path)
+    peaks = load_peaks()
+    flops_clip, bytes_clip = flops_bytes_per_clip(dims)
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.relu(torch.randn((BATCH, dims.C) + dims.spatial, device=dev, generator=g)).bfloat16()
+    dims_struct = model._rt.make_dims(x, model.kernel_path)[0]
+    tc = bool(lib.pasn_tcgen05_supported(dims_struct)) and args.path != "generic"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---------------- device-resident head forward ----------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(x)
+        l0 = lib.pasn_debug_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = model(x)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = int(lib.pasn_debug_launch_count() - l0)
+        # dominant kernel, per launch, CUDA events recorded inside the library on the launch stream
+        lib.pasn_debug_time_main_kernel(1)
+        main_ms = []
+        for _ in range(args.steps):
+            model(x)
+            main_ms.append(float(lib.pasn_debug_last_main_kernel_ms()))
+        lib.pasn_debug_time_main_kernel(0)
+    ms_step = max_over_ranks(ms_total / args.steps)
+    value = world * BATCH / (ms_step * 1e-3)
+    main_ms_avg = float(np.mean(main_ms))
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    x_host = x.cpu().pin_memory()
+    lg_host = torch.empty((BATCH, dims.K), dtype=torch.float32).pin_memory()
+    sm_host = torch.empty((BATCH, dims.P), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty_like(x)
+    e2e_steps = max(3, min(args.steps, 10))
+    with torch.no_grad():
+        for _ in range(2):
+            x_dev.copy_(x_host, non_blocking=True)
+            model(x_dev)
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            x_dev.copy_(x_host, non_blocking=True)
+            logits, sim, occ = model(x_dev)
+            lg_host.copy_(logits, non_blocking=True)
+            sm_host.copy_(sim, non_blocking=True)
+        e1.record()
+        barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+    e2e = {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "clips/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(x_host.numel() * 2), "d2h_bytes_per_step": int(lg_host.numel() * 4 + sm_host.numel() * 4),
+           "api": "Video_XProtoNet.forward(features) on pinned host input; logits+similarity copied back"}
+    del x_host, x_dev
+
+    # ---------------- push over PUSH_CLIPS clips sharded across ranks ----------------
+    push = None
+    if not args.no_push:
+        n_total = args.push_clips
+        lo, hi = synth.shard_range(n_total, rank, world)
+        labels_all = synth.push_labels(n_total, dims.K - 1, seed=7)
+        feats = torch.empty((hi - lo, dims.C) + dims.spatial, dtype=torch.bfloat16, device=dev)
+        pos = lo
+        while pos < hi:  # chunk c holds global clips [c*1000, (c+1)*1000); identical for any sharding
+            c = pos // synth.PUSH_CHUNK
+            gg = torch.Generator(device=dev).manual_seed(1000 + c)
+            chunk = torch.relu(torch.randn((synth.PUSH_CHUNK, dims.C) + dims.spatial, device=dev, generator=gg)).bfloat16()
+            a, b = pos - c * synth.PUSH_CHUNK, min(hi, (c + 1) * synth.PUSH_CHUNK) - c * synth.PUSH_CHUNK
+            feats[pos - lo: pos - lo + (b - a)] = chunk[a:b]
+            pos += b - a
+        del chunk
+        labels = torch.from_numpy(labels_all[lo:hi]).to(dev)
+        proto0 = model.prototype_vectors.data.clone()
+        times, idx_ref = [], None
+        with torch.no_grad():
+            for it in range(1 + 3):
+                model.prototype_vectors.data.copy_(proto0)
+                barrier()
+                e0.record()
+                res = push_resident(model, feats, labels, global_offset=lo, chunk=2048, replace_prototypes=True)
+                e1.record()
+                barrier()
+                if it > 0:
+                    times.append(e0.elapsed_time(e1))
+                if idx_ref is None:
+                    idx_ref = res["index"].clone()
+                assert torch.equal(idx_ref, res["index"])
+        push_ms = max_over_ranks(float(np.mean(times)))
+        f_push = n_total * (flops_clip - 0)  # same head FLOPs per clip (no occurrence-map store)
+        push = {"seconds_per_50k": push_ms * 1e-3 * (50000 / n_total), "clips": n_total, "ms": push_ms, "n_gpus": world,
+                "clips_per_sec": n_total / (push_ms * 1e-3), "scaling": "strong",
+                "tensor_frac_of_sustained": f_push / (push_ms * 1e-3) / 1e12 / (world * peaks["bf16_tflops_sustained"]),
+                "winners_sample": idx_ref[:8].tolist(), "collectives_per_push": 2 if world > 1 else 0}
+        model.prototype_vectors.data.copy_(proto0)
+        del feats
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- CPU baseline (rank 0, N == 1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, n_clips, runs = cpu_port_clips_per_sec(dims, sd, 256, 10.0, 12, cores)
+        cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+               "sample": f"{n_clips} clips per run in chunks of 64 (cfg-3 shape, fp32, torch CPU ops of the reference), "
+                         f"median of {runs} runs"}
+
+    if rank == 0:
+        achieved_tf = BATCH * flops_clip / (main_ms_avg * 1e-3) / 1e12
+        timed_s = ms_step * args.steps * 1e-3
+        peak = peaks["bf16_tflops"] if timed_s < 1.0 else peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": "head_fwd_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: video prototype head fwd, batch {BATCH} per GPU, feature map 512x4x7x7 bf16 "
+                                   "(NCDHW), D=256 P=40 K=4, weights bf16-rounded, fp32 accumulate",
+                       "batch_per_gpu": BATCH, "layout": "NCDHW", "kernel_path": "tcgen05" if tc else "generic",
+                       "l2": "input 205 MB per step > 126 MB L2: re-read from HBM every step"},
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}), "
+                                        + ("burst" if timed_s < 1.0 else "sustained"),
+                         "frac_of_sustained": achieved_tf / peaks["bf16_tflops_sustained"],
+                         "kernel_ms": main_ms_avg, "algorithmic_flop_per_clip": flops_clip,
+                         "hbm_gbs": BATCH * bytes_clip / (main_ms_avg * 1e-3) / 1e9,
+                         "hbm_frac": BATCH * bytes_clip / (main_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "push": push,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

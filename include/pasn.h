@@ -1,0 +1,151 @@
+/* pasn.h -- C ABI of the B200-native ProtoASNet prototype head / push library (libpasn_b200.so).
+ *
+ * The reference (hooman007/ProtoASNet) has no FFI layer: its boundary for this path is the Python
+ * duck-type of the model object.  Each entry point below names the reference
+ * method(s) it replaces; citations are relative to the reference checkout.  The Python module
+ * protoasnet_b200/head.py binds these with ctypes and re-exposes the reference's
+ * forward() / push_forward() / compute_occurence_map() / push_prototypes() API; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all buffers
+ *   - all calls are asynchronous on `stream`, never allocate, never synchronise, never throw
+ *   - return value 0 on success, a negative pasn_status otherwise (pasn_strerror() explains it)
+ *   - the library is stateless; one call sequence per stream at a time
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device the compute calls fail
+ */
+#ifndef PASN_H_
+#define PASN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PASN_ABI_VERSION 1
+
+typedef enum {
+  PASN_OK = 0,
+  PASN_ERR_INVALID = -1,     /* bad argument / unsupported shape                      */
+  PASN_ERR_WORKSPACE = -2,   /* workspace too small                                   */
+  PASN_ERR_CUDA = -3,        /* a CUDA runtime call or kernel launch failed           */
+  PASN_ERR_UNSUPPORTED = -4, /* requested path (e.g. tcgen05) not available for dims  */
+  PASN_ERR_ALIGN = -5        /* pointer not aligned as required                       */
+} pasn_status;
+
+typedef enum { PASN_F32 = 0, PASN_BF16 = 1 } pasn_dtype;
+
+/* memory format of the backbone feature map handed to the head */
+typedef enum {
+  PASN_LAYOUT_NCS = 0, /* contiguous NCDHW / NCHW: [N][C][S], S = T*H*W innermost (reference default) */
+  PASN_LAYOUT_NSC = 1  /* channels_last(_3d):     [N][S][C], C innermost                              */
+} pasn_layout;
+
+/* activation applied to the occurrence module output.  The reference uses abs
+ * (src/models/Video_XProtoNet.py:106-109); nothing else is implemented. */
+typedef enum { PASN_OCC_ABS = 0 } pasn_occ_act;
+
+/* which kernel family computes the head */
+typedef enum {
+  PASN_PATH_AUTO = 0,    /* tcgen05 when dims/dtype qualify, else generic                    */
+  PASN_PATH_GENERIC = 1, /* CUDA-core FFMA kernels, fp32 accumulate, every shape/dtype       */
+  PASN_PATH_TCGEN05 = 2  /* fused tcgen05/TMEM kernel (bf16 operands, fp32 accumulate)       */
+} pasn_path;
+
+typedef struct {
+  int32_t N; /* clips (or images) in this call                                  */
+  int32_t C; /* backbone output channels                                        */
+  int32_t D; /* prototype_shape[1]                                              */
+  int32_t P; /* prototype_shape[0] (number of prototypes)                       */
+  int32_t K; /* num_classes (including the abstention class)                    */
+  int32_t S; /* T*H*W (video) or H*W (image)                                    */
+  int32_t dtype;   /* pasn_dtype of feat and of occurrence_map                  */
+  int32_t layout;  /* pasn_layout of feat                                       */
+  int32_t occ_act; /* pasn_occ_act                                              */
+  int32_t path;    /* pasn_path                                                 */
+} pasn_dims;
+
+/* fp32 master parameters exactly as they sit in the reference state_dict (1x1 kernels flattened):
+ *   add_on_layers.{0,2}.{weight,bias}, occurrence_module.{0,2}.{weight,bias}, occurrence_module.4.weight,
+ *   prototype_vectors, last_layer.weight
+ * (src/models/Video_XProtoNet.py:27-80; src/models/XProtoNet.py:17-49).  In PASN_BF16 mode the conv
+ * weights and biases are rounded to bf16 (round-to-nearest-even) on the fly; prototypes and
+ * last_layer always stay fp32. */
+typedef struct {
+  const float* addon_w1; /* [D][C]   */
+  const float* addon_b1; /* [D]      */
+  const float* addon_w2; /* [D][D]   */
+  const float* addon_b2; /* [D]      */
+  const float* occ_w1;   /* [D][C]   */
+  const float* occ_b1;   /* [D]      */
+  const float* occ_w2;   /* [D/2][D] */
+  const float* occ_b2;   /* [D/2]    */
+  const float* occ_w3;   /* [P][D/2] (bias-free) */
+  const float* prototypes; /* [P][D] */
+  const float* last_layer; /* [K][P] */
+} pasn_weights;
+
+/* optional push arguments of pasn_head_forward: fuse the class-restricted running argmin of
+ * src/utils/push_abs_revision.py:288-307 into the similarity kernel. */
+typedef struct {
+  const int64_t* labels;      /* [N] ground-truth class of each clip (data_sample["target_AS"])        */
+  const int32_t* proto_class; /* [P] class a prototype is restricted to, or -1 for unrestricted        */
+                              /*     (abstention prototypes, push_abs_revision.py:231-237)             */
+  int64_t global_offset;      /* global index of clip 0 of this call in the unshuffled training set    */
+  uint64_t* best_key;         /* [P] in/out running minimum of (orderable(dist) << 32 | global index)  */
+} pasn_push_args;
+
+int pasn_abi_version(void);
+const char* pasn_strerror(int status);
+
+/* 1 if the fused tcgen05 kernel can run these dims (dtype bf16, supported C/D/P/S), else 0 */
+int pasn_tcgen05_supported(const pasn_dims* dims);
+
+/* scratch needed by pasn_head_forward / pasn_occurrence_only for these dims */
+size_t pasn_head_workspace_bytes(const pasn_dims* dims);
+
+/* size of / fill the derived bf16 weight cache the tcgen05 path streams (never saved in checkpoints) */
+size_t pasn_packed_weights_bytes(const pasn_dims* dims);
+int pasn_pack_weights(const pasn_weights* w, const pasn_dims* dims, void* packed, void* stream);
+
+/* Replaces Video_XProtoNet.forward / push_forward minus the backbone
+ * (src/models/Video_XProtoNet.py:82-98, :111-130; src/models/XProtoNet.py:51-67, :87-106).
+ *   feat               [N,C,S] or [N,S,C] (dims.layout), dims.dtype
+ *   packed             result of pasn_pack_weights, or NULL (then only the generic path can run)
+ *   logits             [N,K] fp32
+ *   similarity         [N,P] fp32           ((cos+1)/2)
+ *   occurrence_map     [N,P,S] dims.dtype, or NULL to skip the store
+ *   features_extracted [N,P,D] fp32, or NULL
+ *   distance           [N,P] fp32 (= 1 - similarity), or NULL
+ *   push               NULL, or the fused running-argmin arguments                                  */
+int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
+                      float* logits, float* similarity, void* occurrence_map, float* features_extracted,
+                      float* distance, const pasn_push_args* push, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Replaces Video_XProtoNet.compute_occurence_map minus the backbone (src/models/Video_XProtoNet.py:100-109). */
+int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dims* dims, void* occurrence_map,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* push bookkeeping (src/utils/push_abs_revision.py:242, :299-300, :342-346) */
+int pasn_push_init(uint64_t* best_key, int32_t P, void* stream);          /* best_key[:] = +inf / no index */
+int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* index[p] = winner or -1       */
+                     float* distance, void* stream);                      /* distance[p] fp32 (inf if none)*/
+/* prototype_vectors[p,:] = vec[p,:] where valid[p] != 0 (else unchanged) */
+int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_t* valid, int32_t P, int32_t D,
+                               void* stream);
+
+/* measurement hooks used by bench.py (not part of the reference-facing contract):
+ *   launch_count          number of kernels this library has launched in the process so far
+ *   time_main_kernel(1)   record CUDA events around the dominant kernel of every following pasn_head_forward
+ *   last_main_kernel_ms   synchronise on those events and return the last duration (ms), <0 if none        */
+unsigned long long pasn_debug_launch_count(void);
+int pasn_debug_time_main_kernel(int enable);
+float pasn_debug_last_main_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASN_H_ */

@@ -1,0 +1,12 @@
+"""protoasnet_b200 -- B200-native prototype head + push for ProtoASNet.
+
+Public API mirrors the reference's model/push interface:
+    from protoasnet_b200 import Video_XProtoNet, XProtoNet, construct_Video_XProtoNet, construct_XProtoNet, MODELS, build
+    from protoasnet_b200 import push_prototypes
+"""
+from .head import (MODELS, FeatureInput, Video_XProtoNet, XProtoNet, build, construct_Video_XProtoNet,  # noqa: F401
+                   construct_XProtoNet)
+from .push import push_prototypes, push_resident  # noqa: F401
+
+__all__ = ["MODELS", "FeatureInput", "Video_XProtoNet", "XProtoNet", "build", "construct_Video_XProtoNet",
+           "construct_XProtoNet", "push_prototypes", "push_resident"]

@@ -1,0 +1,114 @@
+// extern "C" entry points of libpasn_b200.so (declared in include/pasn.h) and path dispatch.
+#include "common.cuh"
+
+using namespace pasn;
+
+static bool dims_ok(const pasn_dims* d) {
+  if (!d) return false;
+  if (d->N < 0 || d->C <= 0 || d->D <= 0 || d->P <= 0 || d->K <= 0 || d->S <= 0) return false;
+  if (d->D % 2 != 0) return false;  // occurrence_module hidden width is D // 2
+  if (d->dtype != PASN_F32 && d->dtype != PASN_BF16) return false;
+  if (d->layout != PASN_LAYOUT_NCS && d->layout != PASN_LAYOUT_NSC) return false;
+  if (d->occ_act != PASN_OCC_ABS) return false;
+  if (d->path < PASN_PATH_AUTO || d->path > PASN_PATH_TCGEN05) return false;
+  return true;
+}
+
+static bool use_tcgen05(const pasn_dims& d, const void* packed, int* err) {
+  *err = PASN_OK;
+  if (d.path == PASN_PATH_GENERIC) return false;
+  bool ok = sm100_supported(d) && packed != nullptr;
+  if (d.path == PASN_PATH_TCGEN05 && !ok) *err = PASN_ERR_UNSUPPORTED;
+  return ok;
+}
+
+// ---- measurement hooks ------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+static int g_time_main = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+namespace pasn {
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+void main_kernel_begin(cudaStream_t st) {
+  if (!g_time_main) return;
+  if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+  cudaEventRecord(g_ev0, st);
+}
+void main_kernel_end(cudaStream_t st) {
+  if (g_time_main && g_ev1) cudaEventRecord(g_ev1, st);
+}
+}  // namespace pasn
+extern "C" unsigned long long pasn_debug_launch_count(void) { return g_launches; }
+extern "C" int pasn_debug_time_main_kernel(int enable) { g_time_main = enable; return PASN_OK; }
+extern "C" float pasn_debug_last_main_kernel_ms(void) {
+  if (!g_ev0 || !g_ev1) return -1.f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
+
+extern "C" const char* pasn_strerror(int status) {
+  switch (status) {
+    case PASN_OK: return "ok";
+    case PASN_ERR_INVALID: return "invalid argument or unsupported shape";
+    case PASN_ERR_WORKSPACE: return "workspace too small (see pasn_head_workspace_bytes)";
+    case PASN_ERR_CUDA: return "CUDA runtime call or kernel launch failed";
+    case PASN_ERR_UNSUPPORTED: return "requested kernel path is not available for these dims";
+    case PASN_ERR_ALIGN: return "pointer alignment requirement violated";
+    default: return "unknown pasn status";
+  }
+}
+
+extern "C" int pasn_tcgen05_supported(const pasn_dims* dims) {
+  if (!dims_ok(dims)) return 0;
+  return sm100_supported(*dims) ? 1 : 0;
+}
+
+extern "C" size_t pasn_head_workspace_bytes(const pasn_dims* dims) {
+  if (!dims_ok(dims)) return 0;
+  size_t g = generic_workspace_bytes(*dims);
+  size_t t = (dims->path != PASN_PATH_GENERIC && sm100_supported(*dims)) ? sm100_workspace_bytes(*dims) : 0;
+  if (dims->path == PASN_PATH_TCGEN05) return t;
+  if (dims->path == PASN_PATH_GENERIC) return g;
+  return g > t ? g : t;
+}
+
+extern "C" size_t pasn_packed_weights_bytes(const pasn_dims* dims) {
+  if (!dims_ok(dims) || !sm100_supported(*dims)) return 0;
+  return sm100_packed_bytes(*dims);
+}
+
+extern "C" int pasn_pack_weights(const pasn_weights* w, const pasn_dims* dims, void* packed, void* stream) {
+  if (!w || !dims_ok(dims) || !packed) return PASN_ERR_INVALID;
+  if (!sm100_supported(*dims)) return PASN_ERR_UNSUPPORTED;
+  return sm100_pack_weights(*w, *dims, packed, (cudaStream_t)stream);
+}
+
+extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
+                                 float* logits, float* similarity, void* occurrence_map, float* features_extracted,
+                                 float* distance, const pasn_push_args* push, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  if (!dims_ok(dims) || !w || !logits || !similarity) return PASN_ERR_INVALID;
+  if (dims->N == 0) return PASN_OK;
+  if (!feat || !workspace) return PASN_ERR_INVALID;
+  if (push && (!push->labels || !push->proto_class || !push->best_key)) return PASN_ERR_INVALID;
+  if (push && (push->global_offset < 0 || push->global_offset + dims->N > 0xFFFFFFFFll)) return PASN_ERR_INVALID;
+  int err;
+  if (use_tcgen05(*dims, packed, &err))
+    return sm100_head_forward(feat, *w, packed, *dims, logits, similarity, occurrence_map, features_extracted,
+                              distance, push, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (err) return err;
+  return generic_head_forward(feat, *w, *dims, logits, similarity, occurrence_map, features_extracted, distance, push,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dims* dims,
+                                    void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dims_ok(dims) || !w || !occurrence_map) return PASN_ERR_INVALID;
+  if (dims->N == 0) return PASN_OK;
+  if (!feat || !workspace) return PASN_ERR_INVALID;
+  pasn_dims d = *dims;
+  return generic_occurrence_only(feat, *w, d, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
+}

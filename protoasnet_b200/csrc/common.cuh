@@ -1,0 +1,85 @@
+// Shared device/host helpers for libpasn_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pasn.h"
+
+namespace pasn {
+
+#define PASN_LAUNCH_CHECK()                           \
+  do {                                                \
+    if (cudaGetLastError() != cudaSuccess) return PASN_ERR_CUDA; \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Monotone map fp32 -> u32 (total order incl. negatives), used for packed argmin keys.
+__host__ __device__ __forceinline__ uint32_t f32_orderable(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float f32_from_orderable(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long pack_key(float dist, uint32_t gidx) {
+  return ((unsigned long long)f32_orderable(dist) << 32) | (unsigned long long)gidx;
+}
+#define PASN_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- generic path (generic.cu) -------------------------------------------------------------
+size_t generic_workspace_bytes(const pasn_dims& d);
+int generic_head_forward(const void* feat, const pasn_weights& w, const pasn_dims& d, float* logits, float* sim,
+                         void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws, size_t ws_bytes,
+                         cudaStream_t st);
+int generic_occurrence_only(const void* feat, const pasn_weights& w, const pasn_dims& d, void* occ, void* ws,
+                            size_t ws_bytes, cudaStream_t st);
+
+// ---- prototype stage (proto_stage.cu): cosine -> (.+1)/2 -> logits -> 1-s -> running argmin keys ----
+int launch_proto_stage(const float* feats /*[N,P,D]*/, const float* protos, const float* last_layer, int N, int P,
+                       int D, int K, float* logits, float* sim, float* dist, const pasn_push_args* push,
+                       cudaStream_t st);
+
+// ---- fused tcgen05 path (head_sm100.cu) -----------------------------------------------------
+bool sm100_supported(const pasn_dims& d);
+size_t sm100_workspace_bytes(const pasn_dims& d);
+size_t sm100_packed_bytes(const pasn_dims& d);
+int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, cudaStream_t st);
+int sm100_head_forward(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, float* logits,
+                       float* sim, void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+
+}  // namespace pasn
+
+// ---- debug / measurement hooks (abi.cu) -----------------------------------------------------
+namespace pasn {
+void count_launch(int n = 1);                     // every kernel launch of the library is counted
+void main_kernel_begin(cudaStream_t st);          // bracket the dominant kernel with CUDA events when enabled
+void main_kernel_end(cudaStream_t st);
+}

@@ -1,0 +1,146 @@
+"""GPU parity of the prototype head (through the C ABI) against the reference goldens and the CPU oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import head_oracle as ho
+from protoasnet_b200 import _lib, synth
+from tests.util import BF16_RTOL, FP32_RTOL, assert_close, build_model, load_golden
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HEAD = sorted(glob.glob(os.path.join(GOLDEN, "head_*.npz")))
+
+
+def _run_all(m, x):
+    with torch.no_grad():
+        logits, sim, occ = m(x)
+        feats, dist, occ2, logits2 = m.push_forward(x)
+        occ3 = m.compute_occurence_map(x)
+    return dict(logits=logits, similarity=sim, occurrence_map=occ, features_extracted=feats, distance=dist,
+                occ2=occ2, occ3=occ3, logits2=logits2)
+
+
+@pytest.mark.parametrize("path", HEAD, ids=[os.path.basename(p)[:-4] for p in HEAD])
+def test_fp32_matches_reference_golden(path):
+    z, r = load_golden(path)
+    dims = synth.CONFIGS[r["config"]]
+    sd = synth.make_head_params(dims, **r["params"])
+    x = synth.make_features(dims, r["n"], seed=r["feature_seed"], bf16_round=r["bf16_round"])
+    m = build_model(dims, sd)
+    out = _run_all(m, torch.from_numpy(x).cuda())
+    assert tuple(out["occurrence_map"].shape) == z["occurrence_map"].shape
+    for k in ("logits", "similarity", "occurrence_map", "features_extracted", "distance"):
+        assert_close(out[k], z[k], FP32_RTOL, k)
+    assert torch.equal(out["distance"], 1 - out["similarity"])
+    assert torch.equal(out["logits"], out["logits2"])
+    assert_close(out["occ3"], z["occurrence_map"], FP32_RTOL, "compute_occurence_map")
+
+
+@pytest.mark.parametrize("case", ["head_cfg3_bf16in"])
+def test_bf16_matches_reference_golden(case):
+    """bf16 mode: oracle = reference in fp32 on bf16-rounded inputs and weights."""
+    z, r = load_golden(os.path.join(GOLDEN, case + ".npz"))
+    dims = synth.CONFIGS[r["config"]]
+    sd = synth.make_head_params(dims, **r["params"])
+    x = synth.make_features(dims, r["n"], seed=r["feature_seed"], bf16_round=True)
+    m = build_model(dims, sd)
+    out = _run_all(m, torch.from_numpy(x).cuda().bfloat16())
+    assert out["occurrence_map"].dtype == torch.bfloat16
+    assert_close(out["logits"], z["logits"], BF16_RTOL, "logits")
+    assert_close(out["similarity"], z["similarity"], BF16_RTOL, "similarity")
+    assert_close(out["features_extracted"], z["features_extracted"], 4e-3, "features_extracted")
+    assert_close(out["occurrence_map"], z["occurrence_map"], 8e-3, "occurrence_map(bf16 storage)")
+
+
+SHAPES = [
+    # C, D, P, K, spatial, n
+    (7, 6, 4, 2, (1, 1, 1), 3),      # S = 1
+    (33, 18, 9, 3, (3, 3, 3), 2),    # nothing a multiple of 8/16
+    (64, 32, 8, 4, (5, 7), 5),       # image head
+    (130, 66, 6, 2, (2, 9, 5), 1),   # dims just over a tile edge
+    (16, 8, 128, 4, (2, 2, 2), 2),   # many prototypes
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+@pytest.mark.parametrize("layout", ["ncs", "nsc"])
+def test_ragged_shapes_and_layouts_vs_oracle(shape, layout):
+    C, D, P, K, spatial, n = shape
+    dims = synth.HeadDims(C, D, P, K, spatial)
+    sd = synth.make_head_params(dims, seed=31, bias_scale=0.1, last_layer_noise=0.2)
+    x = synth.make_features(dims, n, seed=17)
+    tsd = ho.to_torch_sd(sd)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x), tsd)
+        _, rs, _ = ho.head_forward_torch(torch.from_numpy(x), tsd)
+    m = build_model(dims, sd)
+    xg = torch.from_numpy(x).cuda()
+    if layout == "nsc":
+        xg = xg.contiguous(memory_format=torch.channels_last_3d if len(spatial) == 3 else torch.channels_last)
+    out = _run_all(m, xg)
+    assert_close(out["logits"], rl.numpy(), FP32_RTOL, "logits")
+    assert_close(out["similarity"], rs.numpy(), FP32_RTOL, "similarity")
+    assert_close(out["occurrence_map"], ro.numpy(), FP32_RTOL, "occ")
+    assert_close(out["features_extracted"], rf.numpy(), FP32_RTOL, "feats")
+    assert_close(out["distance"], rd.numpy(), FP32_RTOL, "dist")
+
+
+def test_empty_batch_and_errors():
+    dims = synth.CONFIGS["tiny_video"]
+    m = build_model(dims, synth.make_head_params(dims, seed=1))
+    with torch.no_grad():
+        logits, sim, occ = m(torch.zeros((0, dims.C) + dims.spatial, device="cuda"))
+    assert logits.shape == (0, dims.K) and sim.shape == (0, dims.P) and occ.shape[0] == 0
+    with torch.no_grad(), pytest.raises(_lib.PasnError):
+        m(torch.zeros((2, dims.C + 1) + dims.spatial, device="cuda"))          # wrong channel count
+    with torch.no_grad(), pytest.raises(_lib.PasnError):
+        m(torch.zeros((2, dims.C) + dims.spatial, device="cuda", dtype=torch.float16))
+
+
+def test_zero_features_hit_cosine_eps_clamp():
+    """All-zero clip: pooled features are exactly 0 -> the 1e-8 norm clamp path; similarity must be exactly 0.5."""
+    dims = synth.CONFIGS["tiny_video"]
+    m = build_model(dims, synth.make_head_params(dims, seed=3))   # zero biases (reference init)
+    with torch.no_grad():
+        logits, sim, occ = m(torch.zeros((2, dims.C) + dims.spatial, device="cuda"))
+    assert torch.all(sim == 0.5) and torch.all(occ == 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_properties_cfg3(dtype):
+    """BASELINE config 3 at full size (N=1024): size-independent properties + a spot check against the oracle."""
+    dims = synth.CONFIGS["cfg3_video_b1024"]
+    bf = dtype == torch.bfloat16
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=bf)
+    m = build_model(dims, sd)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.relu(torch.randn((1024, dims.C) + dims.spatial, device="cuda", generator=g)).to(dtype)
+    with torch.no_grad():
+        f, d, occ, logits = m.push_forward(x)
+        logits_a, sim_a, _ = m(x)
+        perm = torch.randperm(1024, device="cuda", generator=g)
+        f_p, d_p, occ_p, logits_p = m.push_forward(x[perm])
+        parts = [m.push_forward(x[i:i + 200]) for i in range(0, 1024, 200)]
+    # distance is exactly 1 - similarity; similarity in [0, 1]
+    assert torch.equal(d, 1 - sim_a) and float(sim_a.min()) >= 0 and float(sim_a.max()) <= 1.0 + 1e-6
+    assert torch.equal(logits, logits_a)
+    # clips are independent: permuting / re-chunking the batch permutes / concatenates the outputs
+    tol = FP32_RTOL if not bf else BF16_RTOL
+    assert_close(d_p, d[perm].cpu().numpy(), tol, "perm dist")
+    assert_close(torch.cat([p[1] for p in parts]), d.cpu().numpy(), tol, "chunk dist")
+    assert_close(torch.cat([p[3] for p in parts]), logits.cpu().numpy(), tol, "chunk logits")
+    # logits are the last layer applied to the similarities (linearity check of the epilogue)
+    assert_close(logits, (sim_a.double() @ m.last_layer.weight.double().t()).cpu().numpy(), 1e-6, "logits=W sim")
+    # occurrence map is non-negative (abs) and pooled features reproduce from it: spot check 3 clips vs oracle
+    assert float(occ.float().min()) >= 0
+    idx = [0, 517, 1023]
+    xs = x[idx].float().cpu()
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(xs, ho.to_torch_sd(sd))
+    assert_close(d[idx], rd.numpy(), tol, "dist vs oracle")
+    assert_close(logits[idx], rl.numpy(), tol, "logits vs oracle")
+    assert_close(f[idx], rf.numpy(), tol if not bf else 4e-3, "feats vs oracle")

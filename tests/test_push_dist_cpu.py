@@ -1,0 +1,79 @@
+"""world_size-2 gloo test (CPU) of the host-side push merge: packed-key all-reduce(MIN) with the unsigned-order
+sign flip, ownership by shard range, and the masked all-reduce(SUM) winner-row exchange."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from protoasnet_b200 import push as pushmod
+from protoasnet_b200 import synth
+
+
+def _f32_orderable(d):
+    u = np.asarray(d, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.uint64)
+
+
+def _pack(d, idx):
+    return ((_f32_orderable(d) << np.uint64(32)) | np.asarray(idx, dtype=np.uint64)).astype(np.uint64)
+
+
+def _worker(rank, world, port, n_total, P, D, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.random.Generator(np.random.PCG64(99))
+        dmat = g.random((n_total, P), dtype=np.float32) - np.float32(0.1)      # includes negative distances
+        dmat[3, 1] = dmat[40, 1] = dmat[:, 1].min() - np.float32(0.5)          # exact tie across ranks
+        feats = g.standard_normal((n_total, P, D), dtype=np.float32)
+        lo, hi = synth.shard_range(n_total, rank, world)
+        key = np.full(P, np.uint64(0xFFFFFFFFFFFFFFFF))
+        for n in range(lo, hi):
+            key = np.minimum(key, _pack(dmat[n], np.full(P, n)))
+        key[2] = np.uint64(0xFFFFFFFFFFFFFFFF) if True else key[2]             # prototype 2: no candidate anywhere
+        kt = torch.from_numpy(key.view(np.int64).copy())
+        pushmod.merge_keys(kt)
+        idx, dmin = pushmod.decode_keys(kt)
+        mine = (idx >= lo) & (idx < hi)
+        vec = torch.zeros(P, D)
+        for p in torch.nonzero(mine).flatten().tolist():
+            vec[p] = torch.from_numpy(feats[int(idx[p]), p])
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            ret["idx"], ret["d"], ret["vec"] = idx.numpy(), dmin.numpy(), vec.numpy()
+            exp_idx = dmat.argmin(axis=0)
+            exp_idx[2] = -1
+            ret["exp_idx"], ret["exp_d"] = exp_idx, dmat.min(axis=0)
+            ret["exp_vec"] = np.stack([feats[exp_idx[p], p] if exp_idx[p] >= 0 else np.zeros(D, np.float32) for p in range(P)])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_merge_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, 29517, 64, 6, 5, ret), nprocs=2, join=True)
+    assert np.array_equal(ret["idx"], ret["exp_idx"])
+    assert ret["idx"][1] == 3                                   # cross-rank tie -> lowest global index
+    ok = ret["exp_idx"] >= 0
+    assert np.array_equal(ret["d"][ok], ret["exp_d"][ok]) and np.isinf(ret["d"][2])
+    assert np.array_equal(ret["vec"], ret["exp_vec"])           # masked SUM is exact
+
+
+def test_shard_range_covers_set():
+    for n in (0, 1, 7, 50000):
+        for w in (1, 2, 3, 8):
+            r = [synth.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def test_decode_keys_host_matches_packing():
+    d = np.array([0.25, -1e-7, 0.0, 3.5], dtype=np.float32)
+    k = _pack(d, [5, 6, 7, 8])
+    idx, dd = pushmod.decode_keys(torch.from_numpy(k.view(np.int64).copy()))
+    assert idx.tolist() == [5, 6, 7, 8] and np.array_equal(dd.numpy(), d)
+    order = np.argsort(k)
+    assert order.tolist() == [1, 2, 0, 3]                       # unsigned key order == fp32 order

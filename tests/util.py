@@ -1,0 +1,39 @@
+"""Shared helpers for the GPU parity tests (they call the CUDA path through the C ABI via protoasnet_b200)."""
+import json
+
+import numpy as np
+import torch
+
+import protoasnet_b200 as pasn
+from protoasnet_b200 import synth
+
+FP32_RTOL = 1e-5   # north_star: logits and similarities within 1e-5 relative in fp32
+BF16_RTOL = 1e-3   # ... and 1e-3 relative in bf16
+
+
+def build_model(dims: synth.HeadDims, sd_np, device="cuda", path=None):
+    if dims.ndim == 3:
+        m = pasn.construct_Video_XProtoNet(pasn.FeatureInput(dims.C), pretrained=False,
+                                           prototype_shape=dims.prototype_shape, num_classes=dims.K)
+    else:
+        m = pasn.construct_XProtoNet(pasn.FeatureInput(dims.C), pretrained=False,
+                                     prototype_shape=dims.prototype_shape, num_classes=dims.K)
+    own = m.state_dict()
+    assert set(own.keys()) == set(sd_np.keys())
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()})
+    m = m.to(device).eval()
+    if path is not None:
+        m.kernel_path = path
+    return m
+
+
+def assert_close(got, ref, rtol, name=""):
+    got = got.detach().float().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = float(np.abs(ref).max()) if ref.size else 1.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * scale * 0.1 + 1e-30, err_msg=name)
+
+
+def load_golden(path):
+    z = np.load(path)
+    return z, json.loads(str(z["recipe"]))
