@@ -134,7 +134,7 @@ def test_full_size_properties_cfg3(dtype):
     assert_close(torch.cat([p[1] for p in parts]), d.cpu().numpy(), tol, "chunk dist")
     assert_close(torch.cat([p[3] for p in parts]), logits.cpu().numpy(), tol, "chunk logits")
     # logits are the last layer applied to the similarities (linearity check of the epilogue)
-    assert_close(logits, (sim_a.double() @ m.last_layer.weight.double().t()).cpu().numpy(), 1e-6, "logits=W sim")
+    assert_close(logits, (sim_a.double() @ m.last_layer.weight.detach().double().t()).cpu().numpy(), 1e-6, "logits=W sim")
     # occurrence map is non-negative (abs) and pooled features reproduce from it: spot check 3 clips vs oracle
     assert float(occ.float().min()) >= 0
     idx = [0, 517, 1023]
