@@ -144,6 +144,9 @@ int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_
 unsigned long long pasn_debug_launch_count(void);
 int pasn_debug_time_main_kernel(int enable);
 float pasn_debug_last_main_kernel_ms(void);
+/* synchronises `stream` and returns the bounded-wait error code the fused tcgen05 kernels left in `workspace`
+ * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid) */
+int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream);
 
 #ifdef __cplusplus
 }

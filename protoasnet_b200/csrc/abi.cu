@@ -47,6 +47,11 @@ extern "C" float pasn_debug_last_main_kernel_ms(void) {
   return ms;
 }
 
+extern "C" int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream) {
+  if (!workspace || !dims_ok(dims) || !sm100_supported(*dims)) return 0;
+  return sm100_last_error(workspace, *dims, (cudaStream_t)stream);
+}
+
 extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
 
 extern "C" const char* pasn_strerror(int status) {

@@ -1,10 +1,868 @@
-// placeholder until the fused tcgen05 kernel lands
+// Fused prototype-head kernels for sm_100a (tcgen05 tensor cores, TMEM accumulators, bulk-async weight streaming).
+//
+// Reference computation being replaced (per clip, S = T*H*W voxels; src/models/Video_XProtoNet.py:82-98):
+//     H1 = relu(W1 x + b1)            add_on_layers[0..1]     :27-39
+//     F  = W2 H1 + b2                 add_on_layers[2]
+//     G1 = relu(W3 x + b3); G2 = relu(W4 G1 + b4); O = |W5 G2|   occurrence_module + abs   :42-62, :106-109
+//     FE[p,:] = sum_s O[p,s] F[:,s]   occurrence-weighted pooling   :87
+//     cos / (.+1)/2 / logits          :90-96
+//
+// Algorithmic restructuring (exact in real arithmetic): pooling commutes with the last add-on conv,
+//     FE[p,:] = W2 (sum_s O[p,s] H1[:,s]) + b2 * (sum_s O[p,s]),
+// so W2 is applied to P pooled vectors per clip instead of S voxels (D*D*S -> D*D*P MACs per clip).
+//
+// K1  head_tokens_kernel   one persistent CTA per SM walks a contiguous range of clips in tiles of 128 voxels
+//                          ("tokens" = rows of the MMA M dimension).  Per tile, all on tensor cores:
+//        acc_G = X W3^T, acc_A = X W1^T     (SS MMA, X tile MN-major from NCDHW, weights streamed by cp.async.bulk)
+//        G1 -> TMEM (bf16) -> acc_G2 = G1 W4^T -> G2 -> TMEM -> acc_O = G2 W5^T        (A operand from TMEM)
+//        O = |acc_O| -> occurrence map (global) and the B operand of the pooling MMA
+//        FEpre^T[d, (slot,p)] += H1^T O      (MN-major SS MMA; "slot" separates the <=2 clips a tile touches)
+//      Hidden activations never touch HBM.  Outputs: occurrence_map, FEpre [N,P,D] fp32, Osum [N,P] fp32.
+// K2  proto_w2_kernel      FE = FEpre W2^T + b2 Osum on tensor cores (bf16 hi/lo split of FEpre), then the fp32
+//                          cosine -> (.+1)/2 -> logits -> 1-s -> packed argmin keys chain of proto_stage.cu.
 #include "common.cuh"
+#include "sm100_prims.cuh"
+
 namespace pasn {
-bool sm100_supported(const pasn_dims&) { return false; }
-size_t sm100_workspace_bytes(const pasn_dims&) { return 0; }
-size_t sm100_packed_bytes(const pasn_dims&) { return 0; }
-int sm100_pack_weights(const pasn_weights&, const pasn_dims&, void*, cudaStream_t) { return PASN_ERR_UNSUPPORTED; }
-int sm100_head_forward(const void*, const pasn_weights&, const void*, const pasn_dims&, float*, float*, void*, float*,
-                       float*, const pasn_push_args*, void*, size_t, cudaStream_t) { return PASN_ERR_UNSUPPORTED; }
+using namespace sm100;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int DD = 256;            // prototype depth D handled by this kernel
+constexpr int DH = DD / 2;         // occurrence hidden width
+constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
+constexpr int XSLOTS = 4, WSLOTS = 3;
+constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768, HS_BYTES = 32768;
+constexpr int K1_WARPS = 13;
+constexpr int K1_THREADS = K1_WARPS * 32;
+
+// shared-memory map of K1 (offsets from a 1024-byte aligned base)
+constexpr uint32_t SM_X = 0;
+constexpr uint32_t SM_W = SM_X + XSLOTS * XSLOT_BYTES;            // 65536
+constexpr uint32_t SM_HS = SM_W + WSLOTS * WSLOT_BYTES;           // 163840
+constexpr uint32_t SM_OS = SM_HS + HS_BYTES;                      // 196608
+constexpr uint32_t OS_BYTES_MAX = TILE_M * 2 * PP_MAX * 2;        // 24576
+constexpr uint32_t SM_BIAS = SM_OS + OS_BYTES_MAX;                // 221184  b3[256] b1[256] b4[128] fp32
+constexpr uint32_t SM_BAR = SM_BIAS + (DD + DD + DH) * 4;         // 223744
+constexpr uint32_t SM_MISC = SM_BAR + 32 * 8;                     // 224000
+constexpr uint32_t K1_SMEM = SM_MISC + 64;                        // 224064
+
+// barrier indices
+enum {
+  B_XFULL = 0, B_XEMPTY = 4, B_WFULL = 8, B_WEMPTY = 11, B_L1DONE = 14, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
+  B_OSREADY, B_OSEMPTY, B_HSREADY, B_HSEMPTY, B_FEDONE, B_TMEMFREE, B_COUNT
+};
+static_assert(B_COUNT <= 32, "barrier table");
+
+// packed weight buffer (bf16 stage images + fp32 biases), see sm100_pack_weights
+struct PackedLayout {
+  size_t off_l1, off_w4, off_w5, off_bias, off_w2, off_b2, total;
+};
+__host__ __device__ inline PackedLayout packed_layout(int C) {
+  PackedLayout L;
+  const int nkc = C / 64;
+  L.off_l1 = 0;
+  L.off_w4 = (size_t)2 * nkc * 32768;
+  L.off_w5 = L.off_w4 + 65536;
+  L.off_bias = L.off_w5 + 16384;
+  L.off_w2 = (L.off_bias + (DD + DD + DH) * 4 + 1023) / 1024 * 1024;
+  L.off_b2 = L.off_w2 + 4 * 32768;
+  L.total = L.off_b2 + DD * 4;
+  return L;
 }
+
+struct K1Params {
+  const __nv_bfloat16* feat;   // [N][C][S]
+  const uint8_t* packed;
+  __nv_bfloat16* occ;          // [N][P][S] or null
+  float* fepre;                // [N][P][256]
+  float* osum;                 // [N][P]
+  int N, C, P, S, Ppad, nkc, clips_per_cta;
+  int* err;
+};
+
+struct Ctx {
+  int* err;
+  volatile int* abort_s;
+};
+
+// bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug
+__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*c.abort_s) return false;
+    if (clock64() - t0 > 4000000000ll) {
+      *c.abort_s = 1;
+      atomicCAS(c.err, 0, code);
+      return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+// =================================================================================================
+// K1
+// =================================================================================================
+__global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+  volatile int* abort_s = reinterpret_cast<volatile int*>(smem + SM_MISC + 8);
+  float* sb3 = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* sb1 = sb3 + DD;
+  float* sb4 = sb1 + DD;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c_begin = blockIdx.x * p.clips_per_cta;
+  int ncl = p.N - c_begin;
+  if (ncl > p.clips_per_cta) ncl = p.clips_per_cta;
+  if (ncl <= 0) return;
+  const int S = p.S;
+  const int ntok = ncl * S;
+  const int ntiles = (ntok + TILE_M - 1) / TILE_M;
+  const int NPOOL = 2 * p.Ppad;
+  const PackedLayout PL = packed_layout(p.C);
+  Ctx ctx{p.err, abort_s};
+
+  if ((smem_u32(smem) & 1023u) != 0) {  // swizzled layouts need the 1024-byte alignment we asked for
+    if (tid == 0) atomicCAS(p.err, 0, 900);
+    return;
+  }
+
+  if (tid == 0) {
+    *abort_s = 0;
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars[B_XFULL + i], 2); mbar_init(&bars[B_XEMPTY + i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
+    mbar_init(&bars[B_L1DONE], 1);
+    mbar_init(&bars[B_G1READY], 8);
+    mbar_init(&bars[B_G2DONE], 1);
+    mbar_init(&bars[B_G2READY], 8);
+    mbar_init(&bars[B_ODONE], 1);
+    mbar_init(&bars[B_OSREADY], 8);
+    mbar_init(&bars[B_OSEMPTY], 2);
+    mbar_init(&bars[B_HSREADY], 8);
+    mbar_init(&bars[B_HSEMPTY], 1);
+    mbar_init(&bars[B_FEDONE], 1);
+    mbar_init(&bars[B_TMEMFREE], 8);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_s, 512);
+  {
+    const float* gb = reinterpret_cast<const float*>(p.packed + PL.off_bias);
+    for (int i = tid; i < DD + DD + DH; i += K1_THREADS) sb3[i] = gb[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr_s;
+  const uint32_t x_base = smem_u32(smem + SM_X), w_base = smem_u32(smem + SM_W);
+  const uint32_t hs_base = smem_u32(smem + SM_HS), os_base = smem_u32(smem + SM_OS);
+  const int nkc = p.nkc;
+  const int stages_per_tile = 2 * nkc + 3;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc_l1 = make_idesc_bf16(128, 256, 1, 0);
+      const uint32_t idesc_ts64 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_pool = make_idesc_bf16(128, NPOOL, 1, 1);
+      const uint32_t lbo_os = (uint32_t)(NPOOL / 8) * 128u;
+      uint32_t chunk = 0, wst = 0;
+      bool ok = true;
+      for (int tile = 0; tile < ntiles && ok; ++tile) {
+        const uint32_t tp = tile & 1;
+        if (!(ok = bwait(&bars[B_TMEMFREE], tp ^ 1, ctx, 101))) break;
+        tc_fence_after();
+        // ---- layer 1 of both branches: acc_G (cols 0..255) and acc_A (cols 256..511)
+        for (int kc = 0; kc < nkc && ok; ++kc, ++chunk) {
+          const uint32_t xs = chunk & 3, xph = (chunk >> 2) & 1;
+          if (!(ok = bwait(&bars[B_XFULL + xs], xph, ctx, 102))) break;
+          for (int pass = 0; pass < 2 && ok; ++pass, ++wst) {
+            const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+            if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 103))) break;
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t ad = make_smem_desc(x_base + xs * XSLOT_BYTES + k4 * 2048, 8192, 1024, SWZ_128B);
+              const uint64_t bd = make_smem_desc(w_base + ws * WSLOT_BYTES + k4 * 32, 16, 1024, SWZ_128B);
+              mma_ss(tbase + (pass ? 256u : 0u), ad, bd, idesc_l1, (kc | k4) ? 1u : 0u);
+            }
+            mma_commit(&bars[B_WEMPTY + ws]);
+          }
+          mma_commit(&bars[B_XEMPTY + xs]);
+        }
+        if (!ok) break;
+        mma_commit(&bars[B_L1DONE]);
+        // ---- G2 = G1 W4^T : A from TMEM (G1 bf16 at cols [0,64) and [128,192)), two N=64 halves
+        if (!(ok = bwait(&bars[B_G1READY], tp, ctx, 104))) break;
+        tc_fence_after();
+        for (int st = 0; st < 2 && ok; ++st, ++wst) {
+          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 105))) break;
+          tc_fence_after();
+          for (int kcc = 0; kcc < 2; ++kcc)
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int ks = (2 * st + kcc) * 4 + k4;  // 0..15
+                const uint32_t a_col = ks < 8 ? 8u * ks : 128u + 8u * (ks - 8);
+                const uint64_t bd =
+                    make_smem_desc(w_base + ws * WSLOT_BYTES + kcc * 16384 + h * 8192 + k4 * 32, 16, 1024, SWZ_128B);
+                mma_ts(tbase + 64u + 128u * h, tbase + a_col, bd, idesc_ts64, ks ? 1u : 0u);
+              }
+          mma_commit(&bars[B_WEMPTY + ws]);
+        }
+        if (!ok) break;
+        mma_commit(&bars[B_G2DONE]);
+        // ---- O = G2 W5^T : A from TMEM (G2 bf16 at cols [64,96) and [192,224)), D at cols [0,64)
+        if (!(ok = bwait(&bars[B_G2READY], tp, ctx, 106))) break;
+        {
+          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 107))) break;
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a_col = ks < 4 ? 64u + 8u * ks : 192u + 8u * (ks - 4);
+            const uint64_t bd =
+                make_smem_desc(w_base + ws * WSLOT_BYTES + (ks >> 2) * 8192 + (ks & 3) * 32, 16, 1024, SWZ_128B);
+            mma_ts(tbase + 0u, tbase + a_col, bd, idesc_ts64, ks ? 1u : 0u);
+          }
+          mma_commit(&bars[B_WEMPTY + ws]);
+          ++wst;
+        }
+        mma_commit(&bars[B_ODONE]);
+        // ---- pooling: FEpartial^T[d, (slot,p)] = H1^T O ; d halves at cols [0,NPOOL) and [128,128+NPOOL)
+        if (!(ok = bwait(&bars[B_OSREADY], tp, ctx, 108))) break;
+        for (int half = 0; half < 2 && ok; ++half) {
+          if (!(ok = bwait(&bars[B_HSREADY], (uint32_t)half, ctx, 109))) break;  // use #(2*tile+half) -> parity = half
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ad = make_smem_desc(hs_base + ks * 4096, 2048, 128, SWZ_NONE);
+            const uint64_t bd = make_smem_desc(os_base + ks * 2 * lbo_os, lbo_os, 128, SWZ_NONE);
+            mma_ss(tbase + (half ? 128u : 0u), ad, bd, idesc_pool, ks ? 1u : 0u);
+          }
+          mma_commit(&bars[B_HSEMPTY]);
+        }
+        if (!ok) break;
+        mma_commit(&bars[B_OSEMPTY]);
+        mma_commit(&bars[B_FEDONE]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ weight producer (one thread)
+    if (lane == 0) {
+      uint32_t wst = 0;
+      bool ok = true;
+      for (int tile = 0; tile < ntiles && ok; ++tile) {
+        for (int i = 0; i < stages_per_tile; ++i, ++wst) {
+          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          if (!(ok = bwait(&bars[B_WEMPTY + ws], wph ^ 1, ctx, 201))) break;
+          size_t src;
+          uint32_t bytes = 32768;
+          if (i < 2 * nkc) src = PL.off_l1 + (size_t)i * 32768;
+          else if (i < 2 * nkc + 2) src = PL.off_w4 + (size_t)(i - 2 * nkc) * 32768;
+          else { src = PL.off_w5; bytes = 16384; }
+          mbar_arrive_expect_tx(&bars[B_WFULL + ws], bytes);
+          for (uint32_t o = 0; o < bytes; o += 16384)
+            bulk_g2s(w_base + ws * WSLOT_BYTES + o, p.packed + src + o, 16384, &bars[B_WFULL + ws]);
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ X producers: NCDHW gather -> MN-major SW128
+    const int xw = warp - 2;
+    uint32_t chunk = 0;
+    int pending_slot = -1;
+    bool ok = true;
+    for (int tile = 0; tile < ntiles && ok; ++tile) {
+      const int t = tile * TILE_M + 4 * lane;
+      const bool valid = t < ntok;
+      const int clipl = valid ? t / S : 0;
+      const int s = valid ? t - clipl * S : 0;
+      const __nv_bfloat16* src0 = p.feat + ((size_t)(c_begin + clipl) * p.C) * S + s;
+      for (int kc = 0; kc < nkc; ++kc, ++chunk) {
+        const uint32_t xs = chunk & 3, xph = (chunk >> 2) & 1;
+        if (!(ok = bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301))) break;
+        const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const int kl = xw * 32 + j;
+          cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, kl, 8192), src0 + (size_t)(kc * 64 + kl) * S, valid ? 8u : 0u);
+        }
+        cp_async_commit();
+        if (pending_slot >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_XFULL + pending_slot]);
+        }
+        pending_slot = (int)xs;
+      }
+    }
+    cp_async_wait<0>();
+    if (ok && pending_slot >= 0) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_XFULL + pending_slot]);
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ occurrence column sums (bias term of W2)
+    float acc0 = 0.f, acc1 = 0.f;  // p = lane, p = lane + 32
+    bool ok = true;
+    const unsigned char* os = smem + SM_OS;
+    for (int tile = 0; tile < ntiles && ok; ++tile) {
+      if (!(ok = bwait(&bars[B_OSREADY], tile & 1, ctx, 401))) break;
+      float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};  // [slot]
+      for (int slot = 0; slot < 2; ++slot) {
+        const int n0 = slot * p.Ppad + lane, n1 = n0 + 32;
+        if (lane < p.Ppad)
+          for (int tok = 0; tok < TILE_M; ++tok)
+            s0[slot] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n0, tok, NPOOL)));
+        if (lane + 32 < p.Ppad)
+          for (int tok = 0; tok < TILE_M; ++tok)
+            s1[slot] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n1, tok, NPOOL)));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_OSEMPTY]);
+      const int last_tok = min(tile * TILE_M + TILE_M - 1, ntok - 1);
+      const int first_clip = (tile * TILE_M) / S, last_clip = last_tok / S;
+      acc0 += s0[0]; acc1 += s1[0];
+      if (last_clip > first_clip) {
+        if (lane < p.P) p.osum[(size_t)(c_begin + first_clip) * p.P + lane] = acc0;
+        if (lane + 32 < p.P) p.osum[(size_t)(c_begin + first_clip) * p.P + lane + 32] = acc1;
+        acc0 = s0[1]; acc1 = s1[1];
+      }
+      if ((last_tok + 1) % S == 0) {
+        if (lane < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane] = acc0;
+        if (lane + 32 < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane + 32] = acc1;
+        acc0 = acc1 = 0.f;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 4..11
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int tok = q * 32 + lane;
+    float facc[PP_MAX];
+#pragma unroll
+    for (int i = 0; i < PP_MAX; ++i) facc[i] = 0.f;
+    bool ok = true;
+    for (int tile = 0; tile < ntiles && ok; ++tile) {
+      const uint32_t tp = tile & 1;
+      const int t = tile * TILE_M + tok;
+      const bool valid = t < ntok;
+      const int first_clip = (tile * TILE_M) / S;
+      const int clipl = valid ? t / S : first_clip;
+      const int s = t - clipl * S;
+      const int slot = clipl - first_clip;
+
+      // ---- E1: acc_G -> G1 = relu(. + b3) as bf16, in place (cols [128hh, 128hh+64))
+      if (!(ok = bwait(&bars[B_L1DONE], tp, ctx, 501))) break;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32], pk[16];
+        const int col = 128 * hh + 32 * c;
+        tmem_ld_x32(tbase + lane_base + col, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float f0 = fmaxf(__uint_as_float(r[2 * j]) + sb3[col + 2 * j], 0.f);
+          const float f1 = fmaxf(__uint_as_float(r[2 * j + 1]) + sb3[col + 2 * j + 1], 0.f);
+          pk[j] = pack_bf16x2(f0, f1);
+        }
+        tmem_st_x16(tbase + lane_base + 128 * hh + 16 * c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_G1READY]);
+
+      // ---- E2a / E2b helper: acc_A half hf -> H1 = relu(. + b1) bf16 -> Hs (MN-major no-swizzle [128 tok x 128 d])
+      auto convert_h1 = [&](int hf) -> bool {
+        if (!bwait(&bars[B_HSEMPTY], (uint32_t)(hf ^ 1), ctx, 502)) return false;  // use #(2*tile+hf): parity (hf)^1
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          const int dl = 64 * hh + 32 * c;  // d within this half
+          tmem_ld_x32(tbase + lane_base + 256 + 128 * hf + dl, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int dcol = 128 * hf + dl + 8 * g + 2 * j;
+              const float f0 = fmaxf(__uint_as_float(r[8 * g + 2 * j]) + sb1[dcol], 0.f);
+              const float f1 = fmaxf(__uint_as_float(r[8 * g + 2 * j + 1]) + sb1[dcol + 1], 0.f);
+              w4[j] = pack_bf16x2(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(smem + SM_HS + off_mnmajor_nosw(dl + 8 * g, tok, 128)) =
+                make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_HSREADY]);
+        return true;
+      };
+      if (!(ok = convert_h1(0))) break;
+
+      // ---- E3: acc_G2 half hh -> G2 = relu(. + b4) bf16 in place (cols [64+128hh, +32))
+      if (!(ok = bwait(&bars[B_G2DONE], tp, ctx, 503))) break;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(tbase + lane_base + 64 + 128 * hh + 32 * c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ch = 64 * hh + 32 * c + 2 * j;
+          const float f0 = fmaxf(__uint_as_float(r[2 * j]) + sb4[ch], 0.f);
+          const float f1 = fmaxf(__uint_as_float(r[2 * j + 1]) + sb4[ch + 1], 0.f);
+          pk[j] = pack_bf16x2(f0, f1);
+        }
+        tmem_st_x16(tbase + lane_base + 64 + 128 * hh + 16 * c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_G2READY]);
+
+      // ---- E4: acc_O -> O = |.| -> occurrence map (global, bf16) + Os (pooling B operand, slot-in-N layout)
+      if (!(ok = bwait(&bars[B_ODONE], tp, ctx, 504))) break;
+      tc_fence_after();
+      if (!(ok = bwait(&bars[B_OSEMPTY], tp ^ 1, ctx, 505))) break;
+      {
+        uint32_t r[32];
+        tmem_ld_x32(tbase + lane_base + 32 * hh, r);
+        tmem_ld_wait();
+        const int p0 = 32 * hh;
+        if (p.occ != nullptr && valid) {
+          __nv_bfloat16* orow = p.occ + ((size_t)(c_begin + clipl) * p.P) * S + s;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (p0 + j < p.P) orow[(size_t)(p0 + j) * S] = __float2bfloat16_rn(fabsf(__uint_as_float(r[j])));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (p0 + 8 * g < p.Ppad) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w4[j] = valid ? pack_bf16x2(fabsf(__uint_as_float(r[8 * g + 2 * j])), fabsf(__uint_as_float(r[8 * g + 2 * j + 1])))
+                            : 0u;
+            const int n_data = slot * p.Ppad + p0 + 8 * g, n_zero = (1 - slot) * p.Ppad + p0 + 8 * g;
+            *reinterpret_cast<uint4*>(smem + SM_OS + off_mnmajor_nosw(n_data, tok, NPOOL)) =
+                make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            *reinterpret_cast<uint4*>(smem + SM_OS + off_mnmajor_nosw(n_zero, tok, NPOOL)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_OSREADY]);
+
+      // ---- E2b
+      if (!(ok = convert_h1(1))) break;
+
+      // ---- E5: drain FEpartial^T (lane = d) and accumulate per clip in registers
+      if (!(ok = bwait(&bars[B_FEDONE], tp, ctx, 506))) break;
+      tc_fence_after();
+      {
+        const int last_tok = min(tile * TILE_M + TILE_M - 1, ntok - 1);
+        const int last_clip = last_tok / S;
+        const int d = 128 * hh + tok;
+        const uint32_t fe_col = 128u * hh;
+        float* out_first = p.fepre + ((size_t)(c_begin + first_clip) * p.P) * DD + d;
+        float* out_last = p.fepre + ((size_t)(c_begin + last_clip) * p.P) * DD + d;
+        const bool boundary = last_clip > first_clip;
+        const bool ends = ((last_tok + 1) % S) == 0;
+#pragma unroll
+        for (int g = 0; g < PP_MAX / 8; ++g) {
+          if (8 * g < p.Ppad) {
+            uint32_t a[8], b[8];
+            tmem_ld_x8(tbase + lane_base + fe_col + 8 * g, a);
+            tmem_ld_x8(tbase + lane_base + fe_col + p.Ppad + 8 * g, b);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = facc[8 * g + j] + __uint_as_float(a[j]);
+              if (boundary) {
+                if (8 * g + j < p.P) out_first[(size_t)(8 * g + j) * DD] = v;
+                v = __uint_as_float(b[j]);
+              }
+              if (ends) {
+                if (8 * g + j < p.P) out_last[(size_t)(8 * g + j) * DD] = v;
+                v = 0.f;
+              }
+              facc[8 * g + j] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_TMEMFREE]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+// =================================================================================================
+// K2: FE = FEpre W2^T + b2 Osum (tensor cores), cosine / similarity / logits / distance / push keys (fp32)
+// =================================================================================================
+namespace {
+constexpr int K2_THREADS = 128;
+constexpr uint32_t K2_A_IMG = 16384;                 // [128 rows x 64 k] bf16 K-major SW128
+constexpr uint32_t K2_SM_AHI = 0;                    // 4 images
+constexpr uint32_t K2_SM_ALO = 65536;                // 4 images
+constexpr uint32_t K2_SM_W = 131072;                 // 2 x 32 KB ring ([256 rows x 64 k])
+constexpr uint32_t K2_SM_MISC = K2_SM_W + 65536;     // 196608
+constexpr uint32_t K2_SMEM = K2_SM_MISC + 4096;
+
+struct K2Params {
+  const float* fepre; const float* osum; const uint8_t* packed; size_t off_w2, off_b2;
+  const float* protos; const float* last_layer;
+  float* logits; float* sim; float* dist; float* feats;
+  const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
+  int N, P, K, clips_per_tile, ntiles;
+  int* err;
+};
+}  // namespace
+
+__global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K2_SM_MISC);          // [0..1] w_full, [2] tile mma_done (all threads), [3] ring refill (tid 0)
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + K2_SM_MISC + 64);
+  volatile int* abort_s = reinterpret_cast<volatile int*>(smem + K2_SM_MISC + 72);
+  float* s_sim = reinterpret_cast<float*>(smem + K2_SM_MISC + 128);          // [128]
+  float* s_vn = s_sim + 128;                                                 // [<=64] prototype norms (clamped)
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem + K2_SM_MISC + 1024);  // [<=64]
+  float* s_b2 = reinterpret_cast<float*>(smem + K2_SM_MISC + 2048);          // [256]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Ctx ctx{p.err, abort_s};
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) atomicCAS(p.err, 0, 901);
+    return;
+  }
+  if (tid == 0) {
+    *abort_s = 0;
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_s, 256);
+  for (int i = tid; i < DD; i += K2_THREADS) s_b2[i] = reinterpret_cast<const float*>(p.packed + p.off_b2)[i];
+  if (tid < p.P) s_key[tid] = PASN_KEY_NONE;
+  // prototype norms: warp w handles prototypes w, w+4, ...
+  for (int pp = warp; pp < p.P; pp += 4) {
+    float vv = 0.f;
+    for (int d = lane; d < DD; d += 32) { const float b = p.protos[(size_t)pp * DD + d]; vv = fmaf(b, b, vv); }
+    vv = warp_sum(vv);
+    if (lane == 0) s_vn[pp] = fmaxf(sqrtf(vv), 1e-8f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr_s;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+  const int rows_per_tile = p.clips_per_tile * p.P;
+  uint32_t wuse = 0, it = 0;
+  bool ok = true;
+
+  for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
+    const int clip0 = tile * p.clips_per_tile;
+    int nclip = p.N - clip0;
+    if (nclip > p.clips_per_tile) nclip = p.clips_per_tile;
+    const int nrows = nclip * p.P;
+    // kick off the first two W2 chunk loads
+    if (tid == 0) {
+      for (int kc = 0; kc < 2; ++kc) {
+        mbar_arrive_expect_tx(&bars[kc], 32768);
+        bulk_g2s(smem_u32(smem + K2_SM_W) + kc * 32768, p.packed + p.off_w2 + (size_t)kc * 32768, 16384, &bars[kc]);
+        bulk_g2s(smem_u32(smem + K2_SM_W) + kc * 32768 + 16384, p.packed + p.off_w2 + (size_t)kc * 32768 + 16384, 16384, &bars[kc]);
+      }
+    }
+    // A tile: rows of FEpre -> bf16 hi/lo, K-major SW128 images
+    const float* src = p.fepre + (size_t)clip0 * p.P * DD;
+    for (int r = warp; r < TILE_M; r += 4) {
+      float v[8];
+      if (r < nrows) {
+        const float4 a = *reinterpret_cast<const float4*>(src + (size_t)r * DD + 8 * lane);
+        const float4 b = *reinterpret_cast<const float4*>(src + (size_t)r * DD + 8 * lane + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float h0 = round_bf16(v[2 * j]), h1 = round_bf16(v[2 * j + 1]);
+        hi[j] = pack_bf16x2(h0, h1);
+        lo[j] = pack_bf16x2(v[2 * j] - h0, v[2 * j + 1] - h1);
+      }
+      const int k = 8 * lane;  // 0..255
+      const uint32_t off = (uint32_t)(k >> 6) * K2_A_IMG + off_kmajor_sw128(r, k & 63);
+      *reinterpret_cast<uint4*>(smem + K2_SM_AHI + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(smem + K2_SM_ALO + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      for (int kc = 0; kc < 4 && ok; ++kc, ++wuse) {
+        const uint32_t ws = wuse & 1, wph = (wuse >> 1) & 1;
+        if (!(ok = bwait(&bars[ws], wph, ctx, 601))) break;
+        tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t bd = make_smem_desc(smem_u32(smem + K2_SM_W) + ws * 32768 + k4 * 32, 16, 1024, SWZ_128B);
+          const uint64_t ah = make_smem_desc(smem_u32(smem + K2_SM_AHI) + kc * K2_A_IMG + k4 * 32, 16, 1024, SWZ_128B);
+          const uint64_t al = make_smem_desc(smem_u32(smem + K2_SM_ALO) + kc * K2_A_IMG + k4 * 32, 16, 1024, SWZ_128B);
+          mma_ss(tbase, ah, bd, idesc, (kc | k4) ? 1u : 0u);
+          mma_ss(tbase, al, bd, idesc, 1u);
+        }
+        if (kc + 2 < 4) {  // refill this ring slot with chunk kc+2 once its MMAs retire
+          mma_commit(&bars[3]);
+          if (!(ok = bwait(&bars[3], (it * 2 + kc) & 1, ctx, 602))) break;
+          mbar_arrive_expect_tx(&bars[ws], 32768);
+          bulk_g2s(smem_u32(smem + K2_SM_W) + ws * 32768, p.packed + p.off_w2 + (size_t)(kc + 2) * 32768, 16384, &bars[ws]);
+          bulk_g2s(smem_u32(smem + K2_SM_W) + ws * 32768 + 16384, p.packed + p.off_w2 + (size_t)(kc + 2) * 32768 + 16384, 16384, &bars[ws]);
+        }
+      }
+      if (ok) mma_commit(&bars[2]);
+    }
+    if (!(ok = bwait(&bars[2], it & 1, ctx, 603))) break;
+    tc_fence_after();
+
+    // epilogue: thread = row (clip, p)
+    const int r = tid;
+    const bool rvalid = r < nrows;
+    const int cl = rvalid ? r / p.P : 0, pp = rvalid ? r - cl * p.P : 0;
+    const int n = clip0 + cl;
+    const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
+    const float* vrow = p.protos + (size_t)pp * DD;
+    float ff = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < DD; c += 32) {
+      uint32_t a[32];
+      tmem_ld_x32(tbase + lane_base + c, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float f = fmaf(s_b2[c + j], os, __uint_as_float(a[j]));
+        ff = fmaf(f, f, ff);
+      }
+    }
+    const float nf = fmaxf(sqrtf(ff), 1e-8f);
+    const float nv = s_vn[pp];
+    float dot = 0.f;
+    float* frow = (p.feats && rvalid) ? p.feats + ((size_t)n * p.P + pp) * DD : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < DD; c += 32) {
+      uint32_t a[32];
+      tmem_ld_x32(tbase + lane_base + c, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 v = *reinterpret_cast<const float4*>(vrow + c + 4 * j4);
+        float f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = fmaf(s_b2[c + 4 * j4 + j], os, __uint_as_float(a[4 * j4 + j]));
+        dot = fmaf(f[0] / nf, v.x / nv, dot);
+        dot = fmaf(f[1] / nf, v.y / nv, dot);
+        dot = fmaf(f[2] / nf, v.z / nv, dot);
+        dot = fmaf(f[3] / nf, v.w / nv, dot);
+        if (frow) *reinterpret_cast<float4*>(frow + c + 4 * j4) = make_float4(f[0], f[1], f[2], f[3]);
+      }
+    }
+    const float s = (dot + 1.0f) / 2.0f;
+    const float dd = 1.0f - s;
+    s_sim[r] = rvalid ? s : 0.f;
+    if (rvalid) {
+      p.sim[(size_t)n * p.P + pp] = s;
+      if (p.dist) p.dist[(size_t)n * p.P + pp] = dd;
+      if (p.best_key) {
+        const int pc = p.proto_class[pp];
+        if (pc < 0 || (long long)pc == p.labels[n]) atomicMin(&s_key[pp], pack_key(dd, (uint32_t)(p.global_offset + n)));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid < nclip * p.K) {
+      const int c2 = tid / p.K, k = tid - c2 * p.K;
+      float acc = 0.f;
+      for (int q = 0; q < p.P; ++q) acc = fmaf(s_sim[c2 * p.P + q], p.last_layer[(size_t)k * p.P + q], acc);
+      p.logits[(size_t)(clip0 + c2) * p.K + k] = acc;
+    }
+    __syncthreads();
+  }
+  if (p.best_key && tid < p.P && s_key[tid] != PASN_KEY_NONE) atomicMin(&p.best_key[tid], s_key[tid]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// =================================================================================================
+// weight packing: fp32 state_dict tensors -> bf16 stage images in the exact smem byte order
+// =================================================================================================
+__global__ void pack_weights_kernel(pasn_weights w, int C, int P, uint8_t* out) {
+  const PackedLayout PL = packed_layout(C);
+  const int nkc = C / 64;
+  const size_t n_l1 = (size_t)2 * nkc * 256 * 64, n_w4 = (size_t)4 * 128 * 64, n_w5 = (size_t)2 * 64 * 64;
+  const size_t n_w2 = (size_t)4 * 256 * 64, n_bias = DD + DD + DH, n_b2 = DD;
+  const size_t total = n_l1 + n_w4 + n_w5 + n_w2 + n_bias + n_b2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t j = i;
+    if (j < n_l1) {  // stage = 2*kc + pass; pass 0: occ_w1 (W3), pass 1: addon_w1 (W1); image [256 rows][64 k]
+      const int stage = (int)(j / (256 * 64)), e = (int)(j % (256 * 64));
+      const int r = e / 64, k = e % 64, kc = stage >> 1, pass = stage & 1;
+      const float v = (pass ? w.addon_w1 : w.occ_w1)[(size_t)r * C + kc * 64 + k];
+      *reinterpret_cast<__nv_bfloat16*>(out + PL.off_l1 + (size_t)stage * 32768 + off_kmajor_sw128(r, k)) = __float2bfloat16_rn(v);
+      continue;
+    }
+    j -= n_l1;
+    if (j < n_w4) {  // occ_w2 [128][256]: 4 k-chunk images [128 rows][64 k]
+      const int kc = (int)(j / (128 * 64)), e = (int)(j % (128 * 64)), r = e / 64, k = e % 64;
+      *reinterpret_cast<__nv_bfloat16*>(out + PL.off_w4 + (size_t)kc * 16384 + off_kmajor_sw128(r, k)) =
+          __float2bfloat16_rn(w.occ_w2[(size_t)r * DD + kc * 64 + k]);
+      continue;
+    }
+    j -= n_w4;
+    if (j < n_w5) {  // occ_w3 [P][128] zero-padded to 64 rows: 2 k-chunk images [64 rows][64 k]
+      const int kc = (int)(j / (64 * 64)), e = (int)(j % (64 * 64)), r = e / 64, k = e % 64;
+      const float v = r < P ? w.occ_w3[(size_t)r * DH + kc * 64 + k] : 0.f;
+      *reinterpret_cast<__nv_bfloat16*>(out + PL.off_w5 + (size_t)kc * 8192 + off_kmajor_sw128(r, k)) = __float2bfloat16_rn(v);
+      continue;
+    }
+    j -= n_w5;
+    if (j < n_w2) {  // addon_w2 [256][256]: 4 k-chunk images [256 rows][64 k]
+      const int kc = (int)(j / (256 * 64)), e = (int)(j % (256 * 64)), r = e / 64, k = e % 64;
+      *reinterpret_cast<__nv_bfloat16*>(out + PL.off_w2 + (size_t)kc * 32768 + off_kmajor_sw128(r, k)) =
+          __float2bfloat16_rn(w.addon_w2[(size_t)r * DD + kc * 64 + k]);
+      continue;
+    }
+    j -= n_w2;
+    if (j < n_bias) {  // b3 | b1 | b4, bf16-rounded values kept as fp32
+      float v;
+      if (j < DD) v = w.occ_b1[j];
+      else if (j < 2 * DD) v = w.addon_b1[j - DD];
+      else v = w.occ_b2[j - 2 * DD];
+      reinterpret_cast<float*>(out + PL.off_bias)[j] = round_bf16(v);
+      continue;
+    }
+    j -= n_bias;
+    reinterpret_cast<float*>(out + PL.off_b2)[j] = round_bf16(w.addon_b2[j]);
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+bool sm100_supported(const pasn_dims& d) {
+  if (d.dtype != PASN_BF16 || d.layout != PASN_LAYOUT_NCS) return false;
+  if (d.D != DD) return false;
+  if (d.C % 64 != 0 || d.C < 64 || d.C > 1024) return false;
+  if (d.P < 1 || d.P > PP_MAX) return false;
+  if (d.S % 4 != 0 || d.S < TILE_M) return false;   // a 128-voxel tile may touch at most two clips
+  return true;
+}
+
+size_t sm100_packed_bytes(const pasn_dims& d) { return packed_layout(d.C).total; }
+
+// workspace: FEpre [N][P][256] fp32 | Osum [N][P] fp32 | err int
+size_t sm100_workspace_bytes(const pasn_dims& d) {
+  return align_up((size_t)d.N * d.P * DD * 4, 256) + align_up((size_t)d.N * d.P * 4, 256) + 256;
+}
+
+int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, cudaStream_t st) {
+  if (((uintptr_t)packed & 15) != 0) return PASN_ERR_ALIGN;
+  pack_weights_kernel<<<148 * 4, 256, 0, st>>>(w, d.C, d.P, reinterpret_cast<uint8_t*>(packed));
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+
+int sm100_head_forward(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, float* logits,
+                       float* sim, void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  if (!sm100_supported(d)) return PASN_ERR_UNSUPPORTED;
+  if (ws_bytes < sm100_workspace_bytes(d)) return PASN_ERR_WORKSPACE;
+  if (((uintptr_t)feat & 15) != 0 || ((uintptr_t)packed & 15) != 0) return PASN_ERR_ALIGN;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(head_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(proto_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM) != cudaSuccess)
+      return PASN_ERR_CUDA;
+    attr_done = true;
+  }
+  char* wsp = reinterpret_cast<char*>(ws);
+  float* fepre = reinterpret_cast<float*>(wsp);
+  float* osum = reinterpret_cast<float*>(wsp + align_up((size_t)d.N * d.P * DD * 4, 256));
+  int* err = reinterpret_cast<int*>(reinterpret_cast<char*>(osum) + align_up((size_t)d.N * d.P * 4, 256));
+  if (cudaMemsetAsync(err, 0, 4, st) != cudaSuccess) return PASN_ERR_CUDA;
+
+  const int num_sms = 148;
+  K1Params k1{};
+  k1.feat = reinterpret_cast<const __nv_bfloat16*>(feat);
+  k1.packed = reinterpret_cast<const uint8_t*>(packed);
+  k1.occ = reinterpret_cast<__nv_bfloat16*>(occ);
+  k1.fepre = fepre; k1.osum = osum;
+  k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.Ppad = (d.P + 7) / 8 * 8; k1.nkc = d.C / 64;
+  k1.clips_per_cta = ceil_div(d.N, num_sms);
+  k1.err = err;
+  const int grid1 = ceil_div(d.N, k1.clips_per_cta);
+  main_kernel_begin(st);
+  head_tokens_kernel<<<grid1, K1_THREADS, K1_SMEM, st>>>(k1);
+  PASN_LAUNCH_CHECK();
+  main_kernel_end(st);
+  count_launch();
+
+  const PackedLayout PL = packed_layout(d.C);
+  K2Params k2{};
+  k2.fepre = fepre; k2.osum = osum; k2.packed = k1.packed; k2.off_w2 = PL.off_w2; k2.off_b2 = PL.off_b2;
+  k2.protos = w.prototypes; k2.last_layer = w.last_layer;
+  k2.logits = logits; k2.sim = sim; k2.dist = dist; k2.feats = feats;
+  k2.labels = push ? push->labels : nullptr;
+  k2.proto_class = push ? push->proto_class : nullptr;
+  k2.global_offset = push ? (long long)push->global_offset : 0;
+  k2.best_key = push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
+  k2.N = d.N; k2.P = d.P; k2.K = d.K;
+  k2.clips_per_tile = TILE_M / d.P;
+  k2.ntiles = ceil_div(d.N, k2.clips_per_tile);
+  k2.err = err;
+  const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;
+  proto_w2_kernel<<<grid2, K2_THREADS, K2_SMEM, st>>>(k2);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+
+// surfaced for tests / debugging: non-zero if a kernel hit its bounded-wait limit (protocol bug) on the last call
+int sm100_last_error(const void* ws, const pasn_dims& d, cudaStream_t st) {
+  const char* wsp = reinterpret_cast<const char*>(ws);
+  const int* err = reinterpret_cast<const int*>(wsp + align_up((size_t)d.N * d.P * DD * 4, 256) +
+                                                align_up((size_t)d.N * d.P * 4, 256));
+  int h = 0;
+  if (cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return h;
+}
+
+}  // namespace pasn

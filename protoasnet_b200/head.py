@@ -28,6 +28,11 @@ from . import _lib
 from ._lib import PasnDims, PasnPushArgs, PasnWeights
 
 
+import os as _os
+
+_DEBUG_SYNC = bool(int(_os.environ.get("PASN_DEBUG_SYNC", "0")))  # tests: surface kernel-internal fault codes
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -125,6 +130,11 @@ class _HeadRuntime:
                                            sim.data_ptr(), _ptr(occ), _ptr(feats), _ptr(dist),
                                            C.byref(pa) if pa is not None else None, ws.data_ptr(), ws.numel(), stream)
                 _lib.check(st, "pasn_head_forward")
+                if _DEBUG_SYNC:
+                    code = lib.pasn_debug_sm100_error(ws.data_ptr(), C.byref(dims), stream) if packed is not None else 0
+                    torch.cuda.synchronize(dev)
+                    if code != 0:
+                        raise _lib.PasnError(f"fused tcgen05 kernel reported internal pipeline fault {code}")
         return {"logits": logits, "similarity": sim, "occurrence_map": occ, "features_extracted": feats, "distance": dist}
 
     def occurrence_only(self, x: torch.Tensor) -> torch.Tensor:
