@@ -52,6 +52,8 @@ extern "C" int pasn_debug_sm100_error(const void* workspace, const pasn_dims* di
   return sm100_last_error(workspace, *dims, (cudaStream_t)stream);
 }
 
+extern "C" int pasn_debug_set_trace(void* device_buffer) { sm100_set_trace(device_buffer); return PASN_OK; }
+
 extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
 
 extern "C" const char* pasn_strerror(int status) {

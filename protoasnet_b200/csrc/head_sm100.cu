@@ -15,11 +15,12 @@
 //                          ("tokens" = rows of the MMA M dimension).  Per tile, all on tensor cores:
 //        acc_G = X W3^T, acc_A = X W1^T     (SS MMA, X tile MN-major from NCDHW, weights streamed by cp.async.bulk)
 //        G1 -> TMEM (bf16) -> acc_G2 = G1 W4^T -> G2 -> TMEM -> acc_O = G2 W5^T        (A operand from TMEM)
-//        O = |acc_O| -> occurrence map (global) and the B operand of the pooling MMA
+//        O = |acc_O| -> Os in smem: B operand of the pooling MMA, source of the occurrence-map store and of Osum
 //        FEpre^T[d, (slot,p)] += H1^T O      (MN-major SS MMA; "slot" separates the <=2 clips a tile touches)
-//      Hidden activations never touch HBM.  Outputs: occurrence_map, FEpre [N,P,D] fp32, Osum [N,P] fp32.
-// K2  proto_w2_kernel      FE = FEpre W2^T + b2 Osum on tensor cores (bf16 hi/lo split of FEpre), then the fp32
-//                          cosine -> (.+1)/2 -> logits -> 1-s -> packed argmin keys chain of proto_stage.cu.
+//      Hidden activations never touch HBM.  Outputs: occurrence_map, Osum [N,P] fp32 and FEpre as bf16 hi/lo
+//      operand images (already in the K-major SWIZZLE_128B byte order K2 feeds to its MMAs).
+// K2  proto_w2_kernel      FE = FEpre W2^T + b2 Osum on tensor cores (hi/lo split keeps ~fp32 accuracy), then the fp32
+//                          cosine -> (.+1)/2 -> logits -> 1-s -> packed argmin keys chain (cf. proto_stage.cu).
 #include "common.cuh"
 #include "sm100_prims.cuh"
 
@@ -34,8 +35,9 @@ constexpr int DH = DD / 2;         // occurrence hidden width
 constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
 constexpr int XSLOTS = 4, WSLOTS = 3;
 constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768, HS_BYTES = 32768;
-constexpr int K1_WARPS = 13;
+constexpr int K1_WARPS = 14;
 constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr uint32_t FE_TILE_BYTES = 131072;  // K2 operand images of one 128-row tile: hi 64 KB | lo 64 KB
 
 // shared-memory map of K1 (offsets from a 1024-byte aligned base)
 constexpr uint32_t SM_X = 0;
@@ -48,14 +50,13 @@ constexpr uint32_t SM_BAR = SM_BIAS + (DD + DD + DH) * 4;         // 223744
 constexpr uint32_t SM_MISC = SM_BAR + 32 * 8;                     // 224000
 constexpr uint32_t K1_SMEM = SM_MISC + 64;                        // 224064
 
-// barrier indices
 enum {
   B_XFULL = 0, B_XEMPTY = 4, B_WFULL = 8, B_WEMPTY = 11, B_L1DONE = 14, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
   B_OSREADY, B_OSEMPTY, B_HSREADY, B_HSEMPTY, B_FEDONE, B_TMEMFREE, B_COUNT
 };
 static_assert(B_COUNT <= 32, "barrier table");
 
-// packed weight buffer (bf16 stage images + fp32 biases), see sm100_pack_weights
+// packed weight buffer (bf16 stage images + fp32 biases), see pack_weights_kernel
 struct PackedLayout {
   size_t off_l1, off_w4, off_w5, off_bias, off_w2, off_b2, total;
 };
@@ -76,10 +77,11 @@ struct K1Params {
   const __nv_bfloat16* feat;   // [N][C][S]
   const uint8_t* packed;
   __nv_bfloat16* occ;          // [N][P][S] or null
-  float* fepre;                // [N][P][256]
+  uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile
   float* osum;                 // [N][P]
-  int N, C, P, S, Ppad, nkc, clips_per_cta;
+  int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / P
   int* err;
+  long long* trace;            // optional [2][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
 };
 
 struct Ctx {
@@ -102,11 +104,35 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx&
   return true;
 }
 
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 32 fp32 accumulator columns + bias -> ReLU -> 16 packed bf16x2 (bias: 32 floats in smem, 16-byte aligned)
+__device__ __forceinline__ void bias_relu_pack(const uint32_t (&r)[32], const float* bias, uint32_t* pk) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j4);
+    pk[2 * j4] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 0]) + b.x, __uint_as_float(r[4 * j4 + 1]) + b.y);
+    pk[2 * j4 + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 2]) + b.z, __uint_as_float(r[4 * j4 + 3]) + b.w);
+  }
+}
+
+#define K1_TRACE(role, tile, slot)                                                            \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 16)                                 \
+      p.trace[((role) * 16 + (tile)) * 16 + (slot)] = clock64();                              \
+  } while (0)
+
 }  // namespace
 
 // =================================================================================================
 // K1
 // =================================================================================================
+template <int PP>  // padded prototype count (multiple of 8, <= PP_MAX)
 __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -116,6 +142,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
   float* sb1 = sb3 + DD;
   float* sb4 = sb1 + DD;
 
+  constexpr int NPOOL = 2 * PP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c_begin = blockIdx.x * p.clips_per_cta;
   int ncl = p.N - c_begin;
@@ -124,7 +151,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
   const int S = p.S;
   const int ntok = ncl * S;
   const int ntiles = (ntok + TILE_M - 1) / TILE_M;
-  const int NPOOL = 2 * p.Ppad;
   const PackedLayout PL = packed_layout(p.C);
   Ctx ctx{p.err, abort_s};
 
@@ -143,7 +169,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
     mbar_init(&bars[B_G2READY], 8);
     mbar_init(&bars[B_ODONE], 1);
     mbar_init(&bars[B_OSREADY], 8);
-    mbar_init(&bars[B_OSEMPTY], 2);
+    mbar_init(&bars[B_OSEMPTY], 3);   // pooling MMAs retired + Osum warp + occurrence-map store warp
     mbar_init(&bars[B_HSREADY], 8);
     mbar_init(&bars[B_HSEMPTY], 1);
     mbar_init(&bars[B_FEDONE], 1);
@@ -164,19 +190,26 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
   const int nkc = p.nkc;
   const int stages_per_tile = 2 * nkc + 3;
 
+  // TMEM column map (512 columns x 128 lanes; lane = voxel row of the tile unless noted)
+  //   [  0,256) acc_G fp32  -> G1 bf16 at [0,64) and [192,256) -> acc_O fp32 [0,64) -> FEpartial^T half 0 [0,NPOOL)
+  //   [ 64,192) acc_G2 fp32 -> G2 bf16 at [64,96) and [128,160) -> FEpartial^T half 1 [128,128+NPOOL)  (lane = d)
+  //   [256,512) acc_A fp32 (H1 pre-activation), drained to smem by the epilogue
   if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc_l1 = make_idesc_bf16(128, 256, 1, 0);
-      const uint32_t idesc_ts64 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_g2 = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_pool = make_idesc_bf16(128, NPOOL, 1, 1);
-      const uint32_t lbo_os = (uint32_t)(NPOOL / 8) * 128u;
+      constexpr uint32_t lbo_os = (uint32_t)(NPOOL / 8) * 128u;
       uint32_t chunk = 0, wst = 0;
       bool ok = true;
       for (int tile = 0; tile < ntiles && ok; ++tile) {
         const uint32_t tp = tile & 1;
+        K1_TRACE(0, tile, 0);
         if (!(ok = bwait(&bars[B_TMEMFREE], tp ^ 1, ctx, 101))) break;
         tc_fence_after();
+        K1_TRACE(0, tile, 1);
         // ---- layer 1 of both branches: acc_G (cols 0..255) and acc_A (cols 256..511)
         for (int kc = 0; kc < nkc && ok; ++kc, ++chunk) {
           const uint32_t xs = chunk & 3, xph = (chunk >> 2) & 1;
@@ -197,49 +230,54 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         }
         if (!ok) break;
         mma_commit(&bars[B_L1DONE]);
-        // ---- G2 = G1 W4^T : A from TMEM (G1 bf16 at cols [0,64) and [128,192)), two N=64 halves
+        K1_TRACE(0, tile, 2);
+        // ---- G2 = G1 W4^T : A from TMEM (G1 bf16 at cols [0,64) and [192,256)), D = cols [64,192), N = 128
         if (!(ok = bwait(&bars[B_G1READY], tp, ctx, 104))) break;
         tc_fence_after();
+        K1_TRACE(0, tile, 3);
         for (int st = 0; st < 2 && ok; ++st, ++wst) {
           const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
           if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 105))) break;
           tc_fence_after();
-          for (int kcc = 0; kcc < 2; ++kcc)
-            for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                const int ks = (2 * st + kcc) * 4 + k4;  // 0..15
-                const uint32_t a_col = ks < 8 ? 8u * ks : 128u + 8u * (ks - 8);
-                const uint64_t bd =
-                    make_smem_desc(w_base + ws * WSLOT_BYTES + kcc * 16384 + h * 8192 + k4 * 32, 16, 1024, SWZ_128B);
-                mma_ts(tbase + 64u + 128u * h, tbase + a_col, bd, idesc_ts64, ks ? 1u : 0u);
-              }
+          for (int kk = 0; kk < 8; ++kk) {
+            const int ks = st * 8 + kk;  // 0..15, K-step of 16 channels
+            const uint64_t bd =
+                make_smem_desc(w_base + ws * WSLOT_BYTES + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, SWZ_128B);
+            const uint32_t a_col = ks < 8 ? 8u * ks : 192u + 8u * (ks - 8);
+            mma_ts(tbase + 64u, tbase + a_col, bd, idesc_g2, ks ? 1u : 0u);
+          }
           mma_commit(&bars[B_WEMPTY + ws]);
         }
         if (!ok) break;
         mma_commit(&bars[B_G2DONE]);
-        // ---- O = G2 W5^T : A from TMEM (G2 bf16 at cols [64,96) and [192,224)), D at cols [0,64)
+        K1_TRACE(0, tile, 4);
+        // ---- O = G2 W5^T : A from TMEM (G2 bf16 at cols [64,96) and [128,160)), D at cols [0,64)
         if (!(ok = bwait(&bars[B_G2READY], tp, ctx, 106))) break;
+        K1_TRACE(0, tile, 5);
         {
           const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
           if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 107))) break;
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t a_col = ks < 4 ? 64u + 8u * ks : 192u + 8u * (ks - 4);
+            const uint32_t a_col = ks < 4 ? 64u + 8u * ks : 128u + 8u * (ks - 4);
             const uint64_t bd =
                 make_smem_desc(w_base + ws * WSLOT_BYTES + (ks >> 2) * 8192 + (ks & 3) * 32, 16, 1024, SWZ_128B);
-            mma_ts(tbase + 0u, tbase + a_col, bd, idesc_ts64, ks ? 1u : 0u);
+            mma_ts(tbase + 0u, tbase + a_col, bd, idesc_o, ks ? 1u : 0u);
           }
           mma_commit(&bars[B_WEMPTY + ws]);
           ++wst;
         }
         mma_commit(&bars[B_ODONE]);
+        K1_TRACE(0, tile, 6);
         // ---- pooling: FEpartial^T[d, (slot,p)] = H1^T O ; d halves at cols [0,NPOOL) and [128,128+NPOOL)
         if (!(ok = bwait(&bars[B_OSREADY], tp, ctx, 108))) break;
+        K1_TRACE(0, tile, 7);
         for (int half = 0; half < 2 && ok; ++half) {
-          if (!(ok = bwait(&bars[B_HSREADY], (uint32_t)half, ctx, 109))) break;  // use #(2*tile+half) -> parity = half
+          if (!(ok = bwait(&bars[B_HSREADY], (uint32_t)half, ctx, 109))) break;  // use #(2*tile+half): parity = half
           tc_fence_after();
+          K1_TRACE(0, tile, 8 + half);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t ad = make_smem_desc(hs_base + ks * 4096, 2048, 128, SWZ_NONE);
@@ -251,6 +289,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         if (!ok) break;
         mma_commit(&bars[B_OSEMPTY]);
         mma_commit(&bars[B_FEDONE]);
+        K1_TRACE(0, tile, 10);
       }
     }
   } else if (warp == 1) {
@@ -318,14 +357,23 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
     for (int tile = 0; tile < ntiles && ok; ++tile) {
       if (!(ok = bwait(&bars[B_OSREADY], tile & 1, ctx, 401))) break;
       float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};  // [slot]
+#pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
-        const int n0 = slot * p.Ppad + lane, n1 = n0 + 32;
-        if (lane < p.Ppad)
+        const int n0 = slot * PP + lane, n1 = n0 + 32;
+        if (lane < PP) {
+          float a = 0.f;
+#pragma unroll 8
           for (int tok = 0; tok < TILE_M; ++tok)
-            s0[slot] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n0, tok, NPOOL)));
-        if (lane + 32 < p.Ppad)
+            a += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n0, tok, NPOOL)));
+          s0[slot] = a;
+        }
+        if (lane + 32 < PP) {
+          float a = 0.f;
+#pragma unroll 8
           for (int tok = 0; tok < TILE_M; ++tok)
-            s1[slot] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n1, tok, NPOOL)));
+            a += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(os + off_mnmajor_nosw(n1, tok, NPOOL)));
+          s1[slot] = a;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_OSEMPTY]);
@@ -343,123 +391,161 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         acc0 = acc1 = 0.f;
       }
     }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ occurrence-map store: Os (smem) -> [N][P][S] bf16
+    bool ok = true;
+    const unsigned char* os = smem + SM_OS;
+    for (int tile = 0; tile < ntiles && ok; ++tile) {
+      if (!(ok = bwait(&bars[B_OSREADY], tile & 1, ctx, 402))) break;
+      if (p.occ != nullptr) {
+        const int first_clip = (tile * TILE_M) / S;
+#pragma unroll 1
+        for (int grp = 0; grp < 4; ++grp) {
+          const int tok = grp * 32 + lane;
+          const int t = tile * TILE_M + tok;
+          if (t < ntok) {
+            const int clipl = t / S, s = t - clipl * S, slot = clipl - first_clip;
+            __nv_bfloat16* orow = p.occ + ((size_t)(c_begin + clipl) * p.P) * S + s;
+            const unsigned char* src = os + off_mnmajor_nosw(slot * PP, tok, NPOOL);
+#pragma unroll 8
+            for (int pp = 0; pp < p.P; ++pp)
+              orow[(size_t)pp * S] = *reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_OSEMPTY]);
+    }
   } else {
     // ------------------------------------------------------------------ epilogue warps 4..11
     const int q = warp & 3, hh = (warp - 4) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t tl = tbase + lane_base;
     const int tok = q * 32 + lane;
-    float facc[PP_MAX];
+    float facc[PP];
 #pragma unroll
-    for (int i = 0; i < PP_MAX; ++i) facc[i] = 0.f;
+    for (int i = 0; i < PP; ++i) facc[i] = 0.f;
     bool ok = true;
+
+    // acc_A half hf (64 columns of this warp) -> H1 = relu(. + b1) as 32 packed bf16x2 registers
+    auto h1_convert = [&](int hf, uint32_t* hp) {
+      uint32_t ra[32], rb[32];
+      const uint32_t col = 256u + 128u * hf + 64u * hh;
+      tmem_ld_x32(tl + col, ra);
+      tmem_ld_wait();
+      tmem_ld_x32(tl + col + 32, rb);
+      bias_relu_pack(ra, sb1 + 128 * hf + 64 * hh, hp);
+      tmem_ld_wait();
+      bias_relu_pack(rb, sb1 + 128 * hf + 64 * hh + 32, hp + 16);
+    };
+    // packed H1 -> Hs (MN-major no-swizzle [128 tok x 128 d]) once the pooling MMAs of the previous half retired
+    auto h1_store = [&](int hf, const uint32_t* hp) -> bool {
+      if (!bwait(&bars[B_HSEMPTY], (uint32_t)(hf ^ 1), ctx, 502)) return false;  // use #(2*tile+hf)
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(smem + SM_HS + off_mnmajor_nosw(64 * hh + 8 * g, tok, 128)) =
+            make_uint4(hp[4 * g], hp[4 * g + 1], hp[4 * g + 2], hp[4 * g + 3]);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_HSREADY]);
+      return true;
+    };
+
     for (int tile = 0; tile < ntiles && ok; ++tile) {
       const uint32_t tp = tile & 1;
       const int t = tile * TILE_M + tok;
       const bool valid = t < ntok;
       const int first_clip = (tile * TILE_M) / S;
       const int clipl = valid ? t / S : first_clip;
-      const int s = t - clipl * S;
       const int slot = clipl - first_clip;
+      uint32_t hp[32];
 
-      // ---- E1: acc_G -> G1 = relu(. + b3) as bf16, in place (cols [128hh, 128hh+64))
+      // ---- E1: acc_G -> G1 = relu(. + b3) bf16, in place.  Warp hh=0 walks its four 32-column chunks upwards and packs
+      //      channels 0..127 into cols [0,64); warp hh=1 walks downwards and packs channels 128..255 into [192,256).
+      //      Either order only overwrites columns whose fp32 content was already loaded, and it leaves [64,192)
+      //      free as one contiguous N=128 accumulator for G2.
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 0);
       if (!(ok = bwait(&bars[B_L1DONE], tp, ctx, 501))) break;
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32], pk[16];
-        const int col = 128 * hh + 32 * c;
-        tmem_ld_x32(tbase + lane_base + col, r);
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 1);
+      {
+        // chunk order: hh=0 ascending 0,1,2,3 -> writes [16c,+16); hh=1 descending 3,2,1,0 -> writes [192+16c,+16)
+        uint32_t ra[32], rb[32], pk[16];
+        const int c0 = hh ? 3 : 0, dc = hh ? -1 : 1;
+        const uint32_t src = 128u * hh, dst = hh ? 192u : 0u;
+        tmem_ld_x32(tl + src + 32 * c0, ra);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float f0 = fmaxf(__uint_as_float(r[2 * j]) + sb3[col + 2 * j], 0.f);
-          const float f1 = fmaxf(__uint_as_float(r[2 * j + 1]) + sb3[col + 2 * j + 1], 0.f);
-          pk[j] = pack_bf16x2(f0, f1);
-        }
-        tmem_st_x16(tbase + lane_base + 128 * hh + 16 * c, pk);
+        tmem_ld_x32(tl + src + 32 * (c0 + dc), rb);
+        bias_relu_pack(ra, sb3 + src + 32 * c0, pk);
+        tmem_st_x16(tl + dst + 16 * c0, pk);
+        tmem_ld_wait();
+        tmem_ld_x32(tl + src + 32 * (c0 + 2 * dc), ra);
+        bias_relu_pack(rb, sb3 + src + 32 * (c0 + dc), pk);
+        tmem_st_x16(tl + dst + 16 * (c0 + dc), pk);
+        tmem_ld_wait();
+        tmem_ld_x32(tl + src + 32 * (c0 + 3 * dc), rb);
+        bias_relu_pack(ra, sb3 + src + 32 * (c0 + 2 * dc), pk);
+        tmem_st_x16(tl + dst + 16 * (c0 + 2 * dc), pk);
+        tmem_ld_wait();
+        bias_relu_pack(rb, sb3 + src + 32 * (c0 + 3 * dc), pk);
+        tmem_st_x16(tl + dst + 16 * (c0 + 3 * dc), pk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G1READY]);
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 2);
 
-      // ---- E2a / E2b helper: acc_A half hf -> H1 = relu(. + b1) bf16 -> Hs (MN-major no-swizzle [128 tok x 128 d])
-      auto convert_h1 = [&](int hf) -> bool {
-        if (!bwait(&bars[B_HSEMPTY], (uint32_t)(hf ^ 1), ctx, 502)) return false;  // use #(2*tile+hf): parity (hf)^1
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          const int dl = 64 * hh + 32 * c;  // d within this half
-          tmem_ld_x32(tbase + lane_base + 256 + 128 * hf + dl, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int dcol = 128 * hf + dl + 8 * g + 2 * j;
-              const float f0 = fmaxf(__uint_as_float(r[8 * g + 2 * j]) + sb1[dcol], 0.f);
-              const float f1 = fmaxf(__uint_as_float(r[8 * g + 2 * j + 1]) + sb1[dcol + 1], 0.f);
-              w4[j] = pack_bf16x2(f0, f1);
-            }
-            *reinterpret_cast<uint4*>(smem + SM_HS + off_mnmajor_nosw(dl + 8 * g, tok, 128)) =
-                make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_HSREADY]);
-        return true;
-      };
-      if (!(ok = convert_h1(0))) break;
+      // ---- E2a: first half of H1 -> Hs (overlaps the G2 MMAs)
+      h1_convert(0, hp);
+      if (!(ok = h1_store(0, hp))) break;
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 3);
 
-      // ---- E3: acc_G2 half hh -> G2 = relu(. + b4) bf16 in place (cols [64+128hh, +32))
+      // ---- E3: acc_G2 (cols [64,192)) -> G2 = relu(. + b4) bf16 in place at [64+64hh, +32)
       if (!(ok = bwait(&bars[B_G2DONE], tp, ctx, 503))) break;
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32], pk[16];
-        tmem_ld_x32(tbase + lane_base + 64 + 128 * hh + 32 * c, r);
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 4);
+      {
+        uint32_t ra[32], rb[32], pk[16];
+        const uint32_t col = 64u + 64u * hh;
+        tmem_ld_x32(tl + col, ra);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int ch = 64 * hh + 32 * c + 2 * j;
-          const float f0 = fmaxf(__uint_as_float(r[2 * j]) + sb4[ch], 0.f);
-          const float f1 = fmaxf(__uint_as_float(r[2 * j + 1]) + sb4[ch + 1], 0.f);
-          pk[j] = pack_bf16x2(f0, f1);
-        }
-        tmem_st_x16(tbase + lane_base + 64 + 128 * hh + 16 * c, pk);
+        tmem_ld_x32(tl + col + 32, rb);
+        bias_relu_pack(ra, sb4 + 64 * hh, pk);
+        tmem_st_x16(tl + col, pk);
+        tmem_ld_wait();
+        bias_relu_pack(rb, sb4 + 64 * hh + 32, pk);
+        tmem_st_x16(tl + col + 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G2READY]);
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 5);
 
-      // ---- E4: acc_O -> O = |.| -> occurrence map (global, bf16) + Os (pooling B operand, slot-in-N layout)
+      // ---- E2b (register part): second half of H1, converted while the O MMAs run
+      h1_convert(1, hp);
+
+      // ---- E4: acc_O -> O = |.| bf16 -> Os (pooling B operand, slot-in-N layout; other slot and invalid rows zero)
       if (!(ok = bwait(&bars[B_ODONE], tp, ctx, 504))) break;
       tc_fence_after();
       if (!(ok = bwait(&bars[B_OSEMPTY], tp ^ 1, ctx, 505))) break;
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 6);
       {
         uint32_t r[32];
-        tmem_ld_x32(tbase + lane_base + 32 * hh, r);
+        tmem_ld_x32(tl + 32 * hh, r);
         tmem_ld_wait();
         const int p0 = 32 * hh;
-        if (p.occ != nullptr && valid) {
-          __nv_bfloat16* orow = p.occ + ((size_t)(c_begin + clipl) * p.P) * S + s;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (p0 + j < p.P) orow[(size_t)(p0 + j) * S] = __float2bfloat16_rn(fabsf(__uint_as_float(r[j])));
-        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (p0 + 8 * g < p.Ppad) {
+          if (p0 + 8 * g < PP) {
             uint32_t w4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               w4[j] = valid ? pack_bf16x2(fabsf(__uint_as_float(r[8 * g + 2 * j])), fabsf(__uint_as_float(r[8 * g + 2 * j + 1])))
                             : 0u;
-            const int n_data = slot * p.Ppad + p0 + 8 * g, n_zero = (1 - slot) * p.Ppad + p0 + 8 * g;
+            const int n_data = slot * PP + p0 + 8 * g, n_zero = (1 - slot) * PP + p0 + 8 * g;
             *reinterpret_cast<uint4*>(smem + SM_OS + off_mnmajor_nosw(n_data, tok, NPOOL)) =
                 make_uint4(w4[0], w4[1], w4[2], w4[3]);
             *reinterpret_cast<uint4*>(smem + SM_OS + off_mnmajor_nosw(n_zero, tok, NPOOL)) = make_uint4(0, 0, 0, 0);
@@ -470,48 +556,70 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_OSREADY]);
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 7);
 
-      // ---- E2b
-      if (!(ok = convert_h1(1))) break;
+      // ---- E2b (store part)
+      if (!(ok = h1_store(1, hp))) break;
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 8);
 
-      // ---- E5: drain FEpartial^T (lane = d) and accumulate per clip in registers
+      // ---- E5: drain FEpartial^T (lane = d) into per-clip register accumulators; finished clips leave as bf16 hi/lo
+      //      rows of the K2 operand images
       if (!(ok = bwait(&bars[B_FEDONE], tp, ctx, 506))) break;
       tc_fence_after();
+      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 9);
       {
         const int last_tok = min(tile * TILE_M + TILE_M - 1, ntok - 1);
         const int last_clip = last_tok / S;
-        const int d = 128 * hh + tok;
-        const uint32_t fe_col = 128u * hh;
-        float* out_first = p.fepre + ((size_t)(c_begin + first_clip) * p.P) * DD + d;
-        float* out_last = p.fepre + ((size_t)(c_begin + last_clip) * p.P) * DD + d;
         const bool boundary = last_clip > first_clip;
         const bool ends = ((last_tok + 1) % S) == 0;
+        const int d = 128 * hh + tok;
+        const uint32_t fe = tl + 128u * hh;
+        uint32_t nb[PP];  // slot-1 partial = start of the next clip (only meaningful when `boundary`)
+        {
+          uint32_t a[PP];
 #pragma unroll
-        for (int g = 0; g < PP_MAX / 8; ++g) {
-          if (8 * g < p.Ppad) {
-            uint32_t a[8], b[8];
-            tmem_ld_x8(tbase + lane_base + fe_col + 8 * g, a);
-            tmem_ld_x8(tbase + lane_base + fe_col + p.Ppad + 8 * g, b);
-            tmem_ld_wait();
+          for (int g = 0; g < PP / 8; ++g) tmem_ld_x8(fe + 8 * g, *reinterpret_cast<uint32_t(*)[8]>(&a[8 * g]));
+          if (boundary) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v = facc[8 * g + j] + __uint_as_float(a[j]);
-              if (boundary) {
-                if (8 * g + j < p.P) out_first[(size_t)(8 * g + j) * DD] = v;
-                v = __uint_as_float(b[j]);
-              }
-              if (ends) {
-                if (8 * g + j < p.P) out_last[(size_t)(8 * g + j) * DD] = v;
-                v = 0.f;
-              }
-              facc[8 * g + j] = v;
+            for (int g = 0; g < PP / 8; ++g) tmem_ld_x8(fe + PP + 8 * g, *reinterpret_cast<uint32_t(*)[8]>(&nb[8 * g]));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < PP; ++j) facc[j] += __uint_as_float(a[j]);
+        }
+        // all TMEM reads of this tile are done: hand the accumulators back before the (slow) global flush
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_TMEMFREE]);
+        if (warp == 4 && lane == 0) K1_TRACE(1, tile, 10);
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+          const bool flush = rep == 0 ? boundary : ends;
+          if (!flush) continue;
+          const int clip = c_begin + (rep == 0 ? first_clip : last_clip);
+          const int tile2 = clip / p.cpt;
+          const int rowb = (clip - tile2 * p.cpt) * p.P;
+          uint8_t* img = p.feimg + (size_t)tile2 * FE_TILE_BYTES + (size_t)(d >> 6) * 16384;
+#pragma unroll
+          for (int j = 0; j < PP; ++j) {
+            if (j < p.P) {
+              const float v = facc[j];
+              const __nv_bfloat16 h = __float2bfloat16_rn(v);
+              const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+              const uint32_t off = off_kmajor_sw128(rowb + j, d & 63);
+              *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+              *reinterpret_cast<__nv_bfloat16*>(img + 65536 + off) = l;
             }
+          }
+          if (rep == 0) {
+#pragma unroll
+            for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PP; ++j) facc[j] = 0.f;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_TMEMFREE]);
     }
   }
 
@@ -522,35 +630,37 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
 
 // =================================================================================================
 // K2: FE = FEpre W2^T + b2 Osum (tensor cores), cosine / similarity / logits / distance / push keys (fp32)
+//     warps 0..7 epilogue (row = TMEM lane, two column halves), warp 8 MMA issuer, warp 9 bulk-copy loader
 // =================================================================================================
 namespace {
-constexpr int K2_THREADS = 128;
-constexpr uint32_t K2_A_IMG = 16384;                 // [128 rows x 64 k] bf16 K-major SW128
-constexpr uint32_t K2_SM_AHI = 0;                    // 4 images
-constexpr uint32_t K2_SM_ALO = 65536;                // 4 images
-constexpr uint32_t K2_SM_W = 131072;                 // 2 x 32 KB ring ([256 rows x 64 k])
-constexpr uint32_t K2_SM_MISC = K2_SM_W + 65536;     // 196608
-constexpr uint32_t K2_SMEM = K2_SM_MISC + 4096;
+constexpr int K2_THREADS = 320;
+constexpr uint32_t K2_STAGE = 65536;                 // A_hi chunk 16 KB | A_lo chunk 16 KB | W2 chunk 32 KB
+constexpr uint32_t K2_SM_V = 2 * K2_STAGE;           // prototypes fp32 [P][257]
+constexpr uint32_t K2_V_BYTES = PP_MAX * 257 * 4;    // 49344
+constexpr uint32_t K2_SM_MISC = K2_SM_V + 49408;     // 180480
+constexpr uint32_t K2_SMEM = K2_SM_MISC + 8192;
 
 struct K2Params {
-  const float* fepre; const float* osum; const uint8_t* packed; size_t off_w2, off_b2;
+  const uint8_t* feimg; const float* osum; const uint8_t* packed; size_t off_w2, off_b2;
   const float* protos; const float* last_layer;
   float* logits; float* sim; float* dist; float* feats;
   const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
-  int N, P, K, clips_per_tile, ntiles;
+  int N, P, K, cpt, ntiles;
   int* err;
 };
 }  // namespace
 
 __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K2_SM_MISC);          // [0..1] w_full, [2] tile mma_done (all threads), [3] ring refill (tid 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K2_SM_MISC);   // full[0..1] empty[2..3] accfull[4..5] accempty[6..7]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + K2_SM_MISC + 64);
   volatile int* abort_s = reinterpret_cast<volatile int*>(smem + K2_SM_MISC + 72);
-  float* s_sim = reinterpret_cast<float*>(smem + K2_SM_MISC + 128);          // [128]
-  float* s_vn = s_sim + 128;                                                 // [<=64] prototype norms (clamped)
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem + K2_SM_MISC + 1024);  // [<=64]
-  float* s_b2 = reinterpret_cast<float*>(smem + K2_SM_MISC + 2048);          // [256]
+  float* s_vn = reinterpret_cast<float*>(smem + K2_SM_MISC + 128);             // [64] clamped prototype norms
+  float* s_b2 = reinterpret_cast<float*>(smem + K2_SM_MISC + 512);             // [256]
+  float* s_part = reinterpret_cast<float*>(smem + K2_SM_MISC + 1536);          // [2][128][2] (dot, ff) of column half 1
+  float* s_sim = reinterpret_cast<float*>(smem + K2_SM_MISC + 3584);           // [2][128]
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem + K2_SM_MISC + 4608);  // [64]
+  float* s_v = reinterpret_cast<float*>(smem + K2_SM_V);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Ctx ctx{p.err, abort_s};
@@ -561,15 +671,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   if (tid == 0) {
     *abort_s = 0;
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 1); mbar_init(&bars[5], 1); mbar_init(&bars[6], 8); mbar_init(&bars[7], 8);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_ptr_s, 256);
+  if (warp == 0) tmem_alloc(tmem_ptr_s, 512);
   for (int i = tid; i < DD; i += K2_THREADS) s_b2[i] = reinterpret_cast<const float*>(p.packed + p.off_b2)[i];
   if (tid < p.P) s_key[tid] = PASN_KEY_NONE;
-  // prototype norms: warp w handles prototypes w, w+4, ...
-  for (int pp = warp; pp < p.P; pp += 4) {
+  for (int i = tid; i < p.P * DD; i += K2_THREADS) s_v[(i >> 8) * 257 + (i & 255)] = p.protos[i];
+  __syncthreads();
+  for (int pp = warp; pp < p.P; pp += K2_THREADS / 32) {
     float vv = 0.f;
-    for (int d = lane; d < DD; d += 32) { const float b = p.protos[(size_t)pp * DD + d]; vv = fmaf(b, b, vv); }
+    for (int d = lane; d < DD; d += 32) { const float b = s_v[pp * 257 + d]; vv = fmaf(b, b, vv); }
     vv = warp_sum(vv);
     if (lane == 0) s_vn[pp] = fmaxf(sqrtf(vv), 1e-8f);
   }
@@ -577,146 +689,139 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr_s;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
-  const int rows_per_tile = p.clips_per_tile * p.P;
-  uint32_t wuse = 0, it = 0;
-  bool ok = true;
+  const uint32_t st_base = smem_u32(smem);
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
-    const int clip0 = tile * p.clips_per_tile;
-    int nclip = p.N - clip0;
-    if (nclip > p.clips_per_tile) nclip = p.clips_per_tile;
-    const int nrows = nclip * p.P;
-    // kick off the first two W2 chunk loads
-    if (tid == 0) {
-      for (int kc = 0; kc < 2; ++kc) {
-        mbar_arrive_expect_tx(&bars[kc], 32768);
-        bulk_g2s(smem_u32(smem + K2_SM_W) + kc * 32768, p.packed + p.off_w2 + (size_t)kc * 32768, 16384, &bars[kc]);
-        bulk_g2s(smem_u32(smem + K2_SM_W) + kc * 32768 + 16384, p.packed + p.off_w2 + (size_t)kc * 32768 + 16384, 16384, &bars[kc]);
+  if (warp == 9) {
+    // ---------------------------------------------------------------- loader
+    if (lane == 0) {
+      uint32_t u = 0;
+      bool ok = true;
+      for (int it = 0; it < my_tiles && ok; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const uint8_t* a_src = p.feimg + (size_t)tile * FE_TILE_BYTES;
+        for (int kc = 0; kc < 4; ++kc, ++u) {
+          const uint32_t s = u & 1, ph = (u >> 1) & 1;
+          if (!(ok = bwait(&bars[2 + s], ph ^ 1, ctx, 611))) break;
+          const uint32_t dst = st_base + s * K2_STAGE;
+          mbar_arrive_expect_tx(&bars[s], K2_STAGE);
+          bulk_g2s(dst, a_src + (size_t)kc * 16384, 16384, &bars[s]);
+          bulk_g2s(dst + 16384, a_src + 65536 + (size_t)kc * 16384, 16384, &bars[s]);
+          bulk_g2s(dst + 32768, p.packed + p.off_w2 + (size_t)kc * 32768, 16384, &bars[s]);
+          bulk_g2s(dst + 49152, p.packed + p.off_w2 + (size_t)kc * 32768 + 16384, 16384, &bars[s]);
+        }
       }
     }
-    // A tile: rows of FEpre -> bf16 hi/lo, K-major SW128 images
-    const float* src = p.fepre + (size_t)clip0 * p.P * DD;
-    for (int r = warp; r < TILE_M; r += 4) {
-      float v[8];
-      if (r < nrows) {
-        const float4 a = *reinterpret_cast<const float4*>(src + (size_t)r * DD + 8 * lane);
-        const float4 b = *reinterpret_cast<const float4*>(src + (size_t)r * DD + 8 * lane + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float h0 = round_bf16(v[2 * j]), h1 = round_bf16(v[2 * j + 1]);
-        hi[j] = pack_bf16x2(h0, h1);
-        lo[j] = pack_bf16x2(v[2 * j] - h0, v[2 * j + 1] - h1);
-      }
-      const int k = 8 * lane;  // 0..255
-      const uint32_t off = (uint32_t)(k >> 6) * K2_A_IMG + off_kmajor_sw128(r, k & 63);
-      *reinterpret_cast<uint4*>(smem + K2_SM_AHI + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(smem + K2_SM_ALO + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-      for (int kc = 0; kc < 4 && ok; ++kc, ++wuse) {
-        const uint32_t ws = wuse & 1, wph = (wuse >> 1) & 1;
-        if (!(ok = bwait(&bars[ws], wph, ctx, 601))) break;
+  } else if (warp == 8) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+      uint32_t u = 0;
+      bool ok = true;
+      for (int it = 0; it < my_tiles && ok; ++it) {
+        const uint32_t buf = it & 1;
+        if (!(ok = bwait(&bars[6 + buf], ((it >> 1) & 1) ^ 1, ctx, 621))) break;
         tc_fence_after();
+        for (int kc = 0; kc < 4 && ok; ++kc, ++u) {
+          const uint32_t s = u & 1, ph = (u >> 1) & 1;
+          if (!(ok = bwait(&bars[s], ph, ctx, 622))) break;
+          tc_fence_after();
+          const uint32_t sb = st_base + s * K2_STAGE;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t bd = make_smem_desc(smem_u32(smem + K2_SM_W) + ws * 32768 + k4 * 32, 16, 1024, SWZ_128B);
-          const uint64_t ah = make_smem_desc(smem_u32(smem + K2_SM_AHI) + kc * K2_A_IMG + k4 * 32, 16, 1024, SWZ_128B);
-          const uint64_t al = make_smem_desc(smem_u32(smem + K2_SM_ALO) + kc * K2_A_IMG + k4 * 32, 16, 1024, SWZ_128B);
-          mma_ss(tbase, ah, bd, idesc, (kc | k4) ? 1u : 0u);
-          mma_ss(tbase, al, bd, idesc, 1u);
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t bd = make_smem_desc(sb + 32768 + k4 * 32, 16, 1024, SWZ_128B);
+            const uint64_t ah = make_smem_desc(sb + k4 * 32, 16, 1024, SWZ_128B);
+            const uint64_t al = make_smem_desc(sb + 16384 + k4 * 32, 16, 1024, SWZ_128B);
+            mma_ss(tbase + 256u * buf, ah, bd, idesc, (kc | k4) ? 1u : 0u);
+            mma_ss(tbase + 256u * buf, al, bd, idesc, 1u);
+          }
+          mma_commit(&bars[2 + s]);
         }
-        if (kc + 2 < 4) {  // refill this ring slot with chunk kc+2 once its MMAs retire
-          mma_commit(&bars[3]);
-          if (!(ok = bwait(&bars[3], (it * 2 + kc) & 1, ctx, 602))) break;
-          mbar_arrive_expect_tx(&bars[ws], 32768);
-          bulk_g2s(smem_u32(smem + K2_SM_W) + ws * 32768, p.packed + p.off_w2 + (size_t)(kc + 2) * 32768, 16384, &bars[ws]);
-          bulk_g2s(smem_u32(smem + K2_SM_W) + ws * 32768 + 16384, p.packed + p.off_w2 + (size_t)(kc + 2) * 32768 + 16384, 16384, &bars[ws]);
-        }
+        if (ok) mma_commit(&bars[4 + buf]);
       }
-      if (ok) mma_commit(&bars[2]);
     }
-    if (!(ok = bwait(&bars[2], it & 1, ctx, 603))) break;
-    tc_fence_after();
-
-    // epilogue: thread = row (clip, p)
-    const int r = tid;
-    const bool rvalid = r < nrows;
-    const int cl = rvalid ? r / p.P : 0, pp = rvalid ? r - cl * p.P : 0;
-    const int n = clip0 + cl;
-    const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
-    const float* vrow = p.protos + (size_t)pp * DD;
-    float ff = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < DD; c += 32) {
-      uint32_t a[32];
-      tmem_ld_x32(tbase + lane_base + c, a);
+  } else {
+    // ---------------------------------------------------------------- epilogue: row r = 32q + lane, columns [128ch, +128)
+    const int q = warp & 3, ch = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane;
+    bool ok = true;
+    for (int it = 0; it < my_tiles && ok; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const uint32_t buf = it & 1;
+      const int clip0 = tile * p.cpt;
+      int nclip = p.N - clip0;
+      if (nclip > p.cpt) nclip = p.cpt;
+      const int nrows = nclip * p.P;
+      const bool rvalid = r < nrows;
+      const int cl = rvalid ? r / p.P : 0, pp = rvalid ? r - cl * p.P : 0;
+      const int n = clip0 + cl;
+      const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
+      const float* vrow = s_v + pp * 257 + 128 * ch;
+      const float* b2 = s_b2 + 128 * ch;
+      float* frow = (p.feats && rvalid) ? p.feats + ((size_t)n * p.P + pp) * DD + 128 * ch : nullptr;
+      if (!(ok = bwait(&bars[4 + buf], (it >> 1) & 1, ctx, 631))) break;
+      tc_fence_after();
+      const uint32_t ta = tbase + lane_base + 256u * buf + 128u * ch;
+      float ff = 0.f, dot = 0.f;
+      uint32_t ra[32], rb[32];
+      tmem_ld_x32(ta, ra);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float f = fmaf(s_b2[c + j], os, __uint_as_float(a[j]));
-        ff = fmaf(f, f, ff);
-      }
-    }
-    const float nf = fmaxf(sqrtf(ff), 1e-8f);
-    const float nv = s_vn[pp];
-    float dot = 0.f;
-    float* frow = (p.feats && rvalid) ? p.feats + ((size_t)n * p.P + pp) * DD : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < DD; c += 32) {
-      uint32_t a[32];
-      tmem_ld_x32(tbase + lane_base + c, a);
-      tmem_ld_wait();
+      for (int c = 0; c < 4; ++c) {
+        uint32_t* cur = (c & 1) ? rb : ra;
+        uint32_t* nxt = (c & 1) ? ra : rb;
+        if (c < 3) tmem_ld_x32(ta + 32 * (c + 1), *reinterpret_cast<uint32_t(*)[32]>(nxt));
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 v = *reinterpret_cast<const float4*>(vrow + c + 4 * j4);
-        float f[4];
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float f[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f[j] = fmaf(s_b2[c + 4 * j4 + j], os, __uint_as_float(a[4 * j4 + j]));
-        dot = fmaf(f[0] / nf, v.x / nv, dot);
-        dot = fmaf(f[1] / nf, v.y / nv, dot);
-        dot = fmaf(f[2] / nf, v.z / nv, dot);
-        dot = fmaf(f[3] / nf, v.w / nv, dot);
-        if (frow) *reinterpret_cast<float4*>(frow + c + 4 * j4) = make_float4(f[0], f[1], f[2], f[3]);
+          for (int j = 0; j < 4; ++j) {
+            f[j] = fmaf(b2[32 * c + 4 * j4 + j], os, __uint_as_float(cur[4 * j4 + j]));
+            ff = fmaf(f[j], f[j], ff);
+            dot = fmaf(f[j], vrow[32 * c + 4 * j4 + j], dot);
+          }
+          if (frow) *reinterpret_cast<float4*>(frow + 32 * c + 4 * j4) = make_float4(f[0], f[1], f[2], f[3]);
+        }
+        if (c < 3) tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[6 + buf]);   // accumulator buffer may be overwritten by tile it+2
+      float* part = s_part + buf * 256;
+      float* ssim = s_sim + buf * 128;
+      if (ch == 1) { part[2 * r] = dot; part[2 * r + 1] = ff; }
+      named_bar_sync(1, 256);
+      if (ch == 0) {
+        dot += part[2 * r];
+        ff += part[2 * r + 1];
+        const float nf = fmaxf(sqrtf(ff), 1e-8f);
+        const float cosv = dot / (nf * s_vn[pp]);
+        const float s = (cosv + 1.0f) / 2.0f;
+        const float dd = 1.0f - s;
+        ssim[r] = rvalid ? s : 0.f;
+        if (rvalid) {
+          p.sim[(size_t)n * p.P + pp] = s;
+          if (p.dist) p.dist[(size_t)n * p.P + pp] = dd;
+          if (p.best_key) {
+            const int pc = p.proto_class[pp];
+            if (pc < 0 || (long long)pc == p.labels[n]) atomicMin(&s_key[pp], pack_key(dd, (uint32_t)(p.global_offset + n)));
+          }
+        }
+      }
+      named_bar_sync(1, 256);
+      if (tid < nclip * p.K) {
+        const int c2 = tid / p.K, k = tid - c2 * p.K;
+        float acc = 0.f;
+        for (int qq = 0; qq < p.P; ++qq) acc = fmaf(ssim[c2 * p.P + qq], p.last_layer[(size_t)k * p.P + qq], acc);
+        p.logits[(size_t)(clip0 + c2) * p.K + k] = acc;
       }
     }
-    const float s = (dot + 1.0f) / 2.0f;
-    const float dd = 1.0f - s;
-    s_sim[r] = rvalid ? s : 0.f;
-    if (rvalid) {
-      p.sim[(size_t)n * p.P + pp] = s;
-      if (p.dist) p.dist[(size_t)n * p.P + pp] = dd;
-      if (p.best_key) {
-        const int pc = p.proto_class[pp];
-        if (pc < 0 || (long long)pc == p.labels[n]) atomicMin(&s_key[pp], pack_key(dd, (uint32_t)(p.global_offset + n)));
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid < nclip * p.K) {
-      const int c2 = tid / p.K, k = tid - c2 * p.K;
-      float acc = 0.f;
-      for (int q = 0; q < p.P; ++q) acc = fmaf(s_sim[c2 * p.P + q], p.last_layer[(size_t)k * p.P + q], acc);
-      p.logits[(size_t)(clip0 + c2) * p.K + k] = acc;
-    }
-    __syncthreads();
   }
-  if (p.best_key && tid < p.P && s_key[tid] != PASN_KEY_NONE) atomicMin(&p.best_key[tid], s_key[tid]);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 256);
+  if (p.best_key && tid < p.P && s_key[tid] != PASN_KEY_NONE) atomicMin(&p.best_key[tid], s_key[tid]);
+  if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 // =================================================================================================
@@ -775,6 +880,9 @@ __global__ void pack_weights_kernel(pasn_weights w, int C, int P, uint8_t* out) 
 // =================================================================================================
 // host side
 // =================================================================================================
+static long long* g_trace = nullptr;
+void sm100_set_trace(void* dev_buf) { g_trace = reinterpret_cast<long long*>(dev_buf); }
+
 bool sm100_supported(const pasn_dims& d) {
   if (d.dtype != PASN_BF16 || d.layout != PASN_LAYOUT_NCS) return false;
   if (d.D != DD) return false;
@@ -786,9 +894,11 @@ bool sm100_supported(const pasn_dims& d) {
 
 size_t sm100_packed_bytes(const pasn_dims& d) { return packed_layout(d.C).total; }
 
-// workspace: FEpre [N][P][256] fp32 | Osum [N][P] fp32 | err int
+static inline int k2_tiles(const pasn_dims& d) { return ceil_div(d.N, TILE_M / d.P); }
+
+// workspace: K2 operand images [ntiles2][128 KB] | Osum [N][P] fp32 | err int
 size_t sm100_workspace_bytes(const pasn_dims& d) {
-  return align_up((size_t)d.N * d.P * DD * 4, 256) + align_up((size_t)d.N * d.P * 4, 256) + 256;
+  return (size_t)k2_tiles(d) * FE_TILE_BYTES + align_up((size_t)d.N * d.P * 4, 256) + 256;
 }
 
 int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, cudaStream_t st) {
@@ -799,22 +909,34 @@ int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, 
   return PASN_OK;
 }
 
+template <int PP>
+static int launch_k1(const K1Params& k1, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(head_tokens_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM) != cudaSuccess)
+      return PASN_ERR_CUDA;
+    attr_done = true;
+  }
+  head_tokens_kernel<PP><<<grid, K1_THREADS, K1_SMEM, st>>>(k1);
+  PASN_LAUNCH_CHECK();
+  return PASN_OK;
+}
+
 int sm100_head_forward(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, float* logits,
                        float* sim, void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws,
                        size_t ws_bytes, cudaStream_t st) {
   if (!sm100_supported(d)) return PASN_ERR_UNSUPPORTED;
   if (ws_bytes < sm100_workspace_bytes(d)) return PASN_ERR_WORKSPACE;
-  if (((uintptr_t)feat & 15) != 0 || ((uintptr_t)packed & 15) != 0) return PASN_ERR_ALIGN;
+  if (((uintptr_t)feat & 15) != 0 || ((uintptr_t)packed & 15) != 0 || ((uintptr_t)ws & 15) != 0) return PASN_ERR_ALIGN;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(head_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(proto_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(proto_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM) != cudaSuccess)
       return PASN_ERR_CUDA;
     attr_done = true;
   }
   char* wsp = reinterpret_cast<char*>(ws);
-  float* fepre = reinterpret_cast<float*>(wsp);
-  float* osum = reinterpret_cast<float*>(wsp + align_up((size_t)d.N * d.P * DD * 4, 256));
+  uint8_t* feimg = reinterpret_cast<uint8_t*>(wsp);
+  float* osum = reinterpret_cast<float*>(wsp + (size_t)k2_tiles(d) * FE_TILE_BYTES);
   int* err = reinterpret_cast<int*>(reinterpret_cast<char*>(osum) + align_up((size_t)d.N * d.P * 4, 256));
   if (cudaMemsetAsync(err, 0, 4, st) != cudaSuccess) return PASN_ERR_CUDA;
 
@@ -823,20 +945,27 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.feat = reinterpret_cast<const __nv_bfloat16*>(feat);
   k1.packed = reinterpret_cast<const uint8_t*>(packed);
   k1.occ = reinterpret_cast<__nv_bfloat16*>(occ);
-  k1.fepre = fepre; k1.osum = osum;
-  k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.Ppad = (d.P + 7) / 8 * 8; k1.nkc = d.C / 64;
+  k1.feimg = feimg; k1.osum = osum;
+  k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.nkc = d.C / 64;
   k1.clips_per_cta = ceil_div(d.N, num_sms);
+  k1.cpt = TILE_M / d.P;
   k1.err = err;
+  k1.trace = g_trace;
   const int grid1 = ceil_div(d.N, k1.clips_per_cta);
+  const int ppad = (d.P + 7) / 8 * 8;
   main_kernel_begin(st);
-  head_tokens_kernel<<<grid1, K1_THREADS, K1_SMEM, st>>>(k1);
-  PASN_LAUNCH_CHECK();
+  int rc;
+  if (ppad <= 16) rc = launch_k1<16>(k1, grid1, st);
+  else if (ppad <= 32) rc = launch_k1<32>(k1, grid1, st);
+  else if (ppad <= 40) rc = launch_k1<40>(k1, grid1, st);
+  else rc = launch_k1<48>(k1, grid1, st);
+  if (rc) return rc;
   main_kernel_end(st);
   count_launch();
 
   const PackedLayout PL = packed_layout(d.C);
   K2Params k2{};
-  k2.fepre = fepre; k2.osum = osum; k2.packed = k1.packed; k2.off_w2 = PL.off_w2; k2.off_b2 = PL.off_b2;
+  k2.feimg = feimg; k2.osum = osum; k2.packed = k1.packed; k2.off_w2 = PL.off_w2; k2.off_b2 = PL.off_b2;
   k2.protos = w.prototypes; k2.last_layer = w.last_layer;
   k2.logits = logits; k2.sim = sim; k2.dist = dist; k2.feats = feats;
   k2.labels = push ? push->labels : nullptr;
@@ -844,8 +973,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.global_offset = push ? (long long)push->global_offset : 0;
   k2.best_key = push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
   k2.N = d.N; k2.P = d.P; k2.K = d.K;
-  k2.clips_per_tile = TILE_M / d.P;
-  k2.ntiles = ceil_div(d.N, k2.clips_per_tile);
+  k2.cpt = TILE_M / d.P;
+  k2.ntiles = k2_tiles(d);
   k2.err = err;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;
   proto_w2_kernel<<<grid2, K2_THREADS, K2_SMEM, st>>>(k2);
@@ -857,8 +986,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
 // surfaced for tests / debugging: non-zero if a kernel hit its bounded-wait limit (protocol bug) on the last call
 int sm100_last_error(const void* ws, const pasn_dims& d, cudaStream_t st) {
   const char* wsp = reinterpret_cast<const char*>(ws);
-  const int* err = reinterpret_cast<const int*>(wsp + align_up((size_t)d.N * d.P * DD * 4, 256) +
-                                                align_up((size_t)d.N * d.P * 4, 256));
+  const int* err = reinterpret_cast<const int*>(wsp + (size_t)k2_tiles(d) * FE_TILE_BYTES + align_up((size_t)d.N * d.P * 4, 256));
   int h = 0;
   if (cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;

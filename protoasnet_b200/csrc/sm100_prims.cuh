@@ -187,6 +187,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// max(x, 0) folded into the conversion (cvt.rn.relu)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ----------------------------------------------------------------------------------------------
 // canonical operand layouts (byte offsets inside one operand image; image base 1024-byte aligned)
 // ----------------------------------------------------------------------------------------------

@@ -53,7 +53,7 @@ def test_bf16_matches_reference_golden(case):
     assert_close(out["logits"], z["logits"], BF16_RTOL, "logits")
     assert_close(out["similarity"], z["similarity"], BF16_RTOL, "similarity")
     assert_close(out["features_extracted"], z["features_extracted"], 4e-3, "features_extracted")
-    assert_close(out["occurrence_map"], z["occurrence_map"], 8e-3, "occurrence_map(bf16 storage)")
+    assert_close(out["occurrence_map"], z["occurrence_map"], 2e-2, "occurrence_map(bf16 storage + bf16 hidden activations)")
 
 
 SHAPES = [
