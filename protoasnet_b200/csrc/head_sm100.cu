@@ -677,7 +677,16 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   if (warp == 0) tmem_alloc(tmem_ptr_s, 512);
   for (int i = tid; i < DD; i += K2_THREADS) s_b2[i] = reinterpret_cast<const float*>(p.packed + p.off_b2)[i];
   if (tid < p.P) s_key[tid] = PASN_KEY_NONE;
-  for (int i = tid; i < p.P * DD; i += K2_THREADS) s_v[(i >> 8) * 257 + (i & 255)] = p.protos[i];
+  {  // prototypes -> smem rows of 257 floats (conflict-free row-per-lane reads); 128-bit loads, several in flight
+    const float4* src = reinterpret_cast<const float4*>(p.protos);
+    const int n4 = p.P * (DD / 4);
+#pragma unroll 4
+    for (int i = tid; i < n4; i += K2_THREADS) {
+      const float4 v = __ldg(src + i);
+      float* dst = s_v + ((i * 4) >> 8) * 257 + ((i * 4) & 255);
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  }
   __syncthreads();
   for (int pp = warp; pp < p.P; pp += K2_THREADS / 32) {
     float vv = 0.f;

@@ -53,7 +53,9 @@ def test_bf16_matches_reference_golden(case):
     assert_close(out["logits"], z["logits"], BF16_RTOL, "logits")
     assert_close(out["similarity"], z["similarity"], BF16_RTOL, "similarity")
     assert_close(out["features_extracted"], z["features_extracted"], 4e-3, "features_extracted")
-    assert_close(out["occurrence_map"], z["occurrence_map"], 2e-2, "occurrence_map(bf16 storage + bf16 hidden activations)")
+    # the map itself is stored in bf16 and computed from bf16 hidden activations: entries are judged against the
+    # map's scale (|.| of a near-zero pre-activation has no meaningful relative error)
+    assert_close(out["occurrence_map"], z["occurrence_map"], 2e-2, "occurrence_map (bf16)", atol_frac=1e-2)
 
 
 SHAPES = [

@@ -120,7 +120,12 @@ def test_push_full_size_properties():
             keys.append(k)
         merged = torch.stack(keys).view(torch.int64)
         merged = ((merged ^ pushmod._SIGN).min(dim=0).values) ^ pushmod._SIGN
-        assert torch.equal(merged, one)
+        # winners are identical for any sharding; the fp32 distance may differ in its last bits because the fused
+        # kernel's pooling order depends on where a clip falls in the 128-voxel tiling of its batch
+        idx_m, dist_m = pushmod.decode_keys(merged)
+        idx_1, dist_1 = pushmod.decode_keys(one)
+        assert torch.equal(idx_m, idx_1)
+        assert float((dist_m - dist_1).abs().max()) < 1e-5
     idx, dist = pushmod.decode_keys(one)
     assert torch.all(y[idx[:30]] == pc[:30].long())             # class restriction holds
     res1 = pushmod.push_resident(m, x, y, chunk=2048)

@@ -27,11 +27,14 @@ def build_model(dims: synth.HeadDims, sd_np, device="cuda", path=None):
     return m
 
 
-def assert_close(got, ref, rtol, name=""):
+def assert_close(got, ref, rtol, name="", atol_frac=None):
+    """|got - ref| <= atol + rtol*|ref| with atol = atol_frac * max|ref| (default rtol/10: near-zero entries of a
+    tensor are judged against the tensor's scale, everything else relatively)."""
     got = got.detach().float().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
     ref = np.asarray(ref, dtype=np.float64)
     scale = float(np.abs(ref).max()) if ref.size else 1.0
-    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * scale * 0.1 + 1e-30, err_msg=name)
+    frac = rtol * 0.1 if atol_frac is None else atol_frac
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=frac * scale + 1e-30, err_msg=name)
 
 
 def load_golden(path):
