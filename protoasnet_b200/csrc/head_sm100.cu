@@ -21,6 +21,8 @@
 //      operand images (already in the K-major SWIZZLE_128B byte order K2 feeds to its MMAs).
 // K2  proto_w2_kernel      FE = FEpre W2^T + b2 Osum on tensor cores (hi/lo split keeps ~fp32 accuracy), then the fp32
 //                          cosine -> (.+1)/2 -> logits -> 1-s -> packed argmin keys chain (cf. proto_stage.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100_prims.cuh"
 
@@ -33,9 +35,14 @@ constexpr int TILE_M = 128;
 constexpr int DD = 256;            // prototype depth D handled by this kernel
 constexpr int DH = DD / 2;         // occurrence hidden width
 constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
-constexpr int XSLOTS = 4, WSLOTS = 3;
+constexpr int XSLOTS = 4;
+#ifndef PASN_WSLOTS
+#define PASN_WSLOTS 3
+#endif
+constexpr int WSLOTS = PASN_WSLOTS;
 constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768, HS_BYTES = 32768;
-constexpr int K1_WARPS = 14;
+constexpr int K1_WARPS = 16;
+constexpr int EPI_WARP0 = 6;   // warps 6..13: epilogue (TMEM quadrant = warp % 4), 14: Osum, 15: occurrence-map store
 constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr uint32_t FE_TILE_BYTES = 131072;  // K2 operand images of one 128-row tile: hi 64 KB | lo 64 KB
 
@@ -52,7 +59,7 @@ constexpr uint32_t K1_SMEM = SM_MISC + 64;                        // 224064
 
 enum {
   B_XFULL = 0, B_XEMPTY = 4, B_WFULL = 8, B_WEMPTY = 11, B_L1DONE = 14, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
-  B_OSREADY, B_OSEMPTY, B_HSREADY, B_HSEMPTY, B_FEDONE, B_TMEMFREE, B_COUNT
+  B_OSREADY, B_OSEMPTY, B_HSREADY, B_HSEMPTY, B_FEDONE, B_TMEMFREE, B_R1FREE, B_COUNT
 };
 static_assert(B_COUNT <= 32, "barrier table");
 
@@ -79,9 +86,10 @@ struct K1Params {
   __nv_bfloat16* occ;          // [N][P][S] or null
   uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile
   float* osum;                 // [N][P]
-  int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / P
+  int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / PP
   int* err;
-  long long* trace;            // optional [2][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
+  long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
+  int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X
 };
 
 struct Ctx {
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
 
   if (tid == 0) {
     *abort_s = 0;
-    for (int i = 0; i < 4; ++i) { mbar_init(&bars[B_XFULL + i], 2); mbar_init(&bars[B_XEMPTY + i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars[B_XFULL + i], 4); mbar_init(&bars[B_XEMPTY + i], 1); }
     for (int i = 0; i < 3; ++i) { mbar_init(&bars[B_WFULL + i], 1); mbar_init(&bars[B_WEMPTY + i], 1); }
     mbar_init(&bars[B_L1DONE], 1);
     mbar_init(&bars[B_G1READY], 8);
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
     mbar_init(&bars[B_HSEMPTY], 1);
     mbar_init(&bars[B_FEDONE], 1);
     mbar_init(&bars[B_TMEMFREE], 8);
+    mbar_init(&bars[B_R1FREE], 8);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_s, 512);
@@ -202,41 +211,76 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_pool = make_idesc_bf16(128, NPOOL, 1, 1);
       constexpr uint32_t lbo_os = (uint32_t)(NPOOL / 8) * 128u;
-      uint32_t chunk = 0, wst = 0;
+      uint32_t wst = 0;
       bool ok = true;
+      // RA = leading 64-channel chunks whose add-on pass (acc_A) is issued ahead of time, during the previous tile's
+      // tail: acc_A's columns are free as soon as the epilogue has pulled H1 into registers, long before acc_G's.
+      const int RA = nkc < 4 ? nkc : 4;
+      long long xwait = 0, wwait = 0;  // cycles the issue thread spent blocked on X chunks / weight stages (trace only)
+      auto wait_x = [&](int tile, int kc) -> bool {
+        const uint32_t g = (uint32_t)(tile * nkc + kc);
+        const long long t0 = clock64();
+        const bool r = bwait(&bars[B_XFULL + (g % XSLOTS)], (g / XSLOTS) & 1, ctx, 102);
+        const long long dt = clock64() - t0;
+        xwait += dt;
+        if (p.trace != nullptr && blockIdx.x == 0 && tile < 16 && kc < 8) p.trace[(2 * 16 + tile) * 16 + kc] = dt;
+        return r;
+      };
+      auto free_x = [&](int tile, int kc) {
+        const uint32_t g = (uint32_t)(tile * nkc + kc);
+        mma_commit(&bars[B_XEMPTY + (g % XSLOTS)]);
+      };
+      auto issue_pass = [&](int tile, int kc, int pass) -> bool {  // 4 MMAs: one chunk into acc_G (pass 0) / acc_A (pass 1)
+        const uint32_t g = (uint32_t)(tile * nkc + kc), xs = g % XSLOTS;
+        const uint32_t ws = wst % WSLOTS, wph = (wst / WSLOTS) & 1;
+        ++wst;
+        const long long t0 = clock64();
+        if (!bwait(&bars[B_WFULL + ws], wph, ctx, 103)) return false;
+        {
+          const long long dt = clock64() - t0;
+          wwait += dt;
+          if (p.trace != nullptr && blockIdx.x == 0 && tile < 16 && kc < 8) p.trace[(2 * 16 + tile) * 16 + 8 + kc] += dt;
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t ad = make_smem_desc(x_base + xs * XSLOT_BYTES + k4 * 2048, 8192, 1024, SWZ_128B);
+          const uint64_t bd = make_smem_desc(w_base + ws * WSLOT_BYTES + k4 * 32, 16, 1024, SWZ_128B);
+          mma_ss(tbase + (pass ? 256u : 0u), ad, bd, idesc_l1, (kc | k4) ? 1u : 0u);
+        }
+        mma_commit(&bars[B_WEMPTY + ws]);
+        return true;
+      };
+      for (int kc = 0; kc < RA && ok; ++kc) ok = wait_x(0, kc) && issue_pass(0, kc, 1);  // tile 0 has no predecessor
       for (int tile = 0; tile < ntiles && ok; ++tile) {
         const uint32_t tp = tile & 1;
         K1_TRACE(0, tile, 0);
-        if (!(ok = bwait(&bars[B_TMEMFREE], tp ^ 1, ctx, 101))) break;
+        if (!(ok = bwait(&bars[B_TMEMFREE], tp ^ 1, ctx, 101))) break;   // acc_G columns drained by the previous tile
         tc_fence_after();
         K1_TRACE(0, tile, 1);
-        // ---- layer 1 of both branches: acc_G (cols 0..255) and acc_A (cols 256..511)
-        for (int kc = 0; kc < nkc && ok; ++kc, ++chunk) {
-          const uint32_t xs = chunk & 3, xph = (chunk >> 2) & 1;
-          if (!(ok = bwait(&bars[B_XFULL + xs], xph, ctx, 102))) break;
-          for (int pass = 0; pass < 2 && ok; ++pass, ++wst) {
-            const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
-            if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 103))) break;
-            tc_fence_after();
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t ad = make_smem_desc(x_base + xs * XSLOT_BYTES + k4 * 2048, 8192, 1024, SWZ_128B);
-              const uint64_t bd = make_smem_desc(w_base + ws * WSLOT_BYTES + k4 * 32, 16, 1024, SWZ_128B);
-              mma_ss(tbase + (pass ? 256u : 0u), ad, bd, idesc_l1, (kc | k4) ? 1u : 0u);
-            }
-            mma_commit(&bars[B_WEMPTY + ws]);
-          }
-          mma_commit(&bars[B_XEMPTY + xs]);
+        // ---- layer 1: acc_G (cols 0..255) for every chunk, acc_A (cols 256..511) for the chunks not issued ahead
+        for (int kc = 0; kc < RA && ok; ++kc) {
+          ok = issue_pass(tile, kc, 0);
+          free_x(tile, kc);
+        }
+        for (int kc = RA; kc < nkc && ok; ++kc) {
+          ok = wait_x(tile, kc) && issue_pass(tile, kc, 0) && issue_pass(tile, kc, 1);
+          free_x(tile, kc);
         }
         if (!ok) break;
         mma_commit(&bars[B_L1DONE]);
         K1_TRACE(0, tile, 2);
+        if (p.trace != nullptr && blockIdx.x == 0 && tile < 16) {
+          p.trace[(0 * 16 + tile) * 16 + 11] = xwait;
+          p.trace[(0 * 16 + tile) * 16 + 12] = wwait;
+        }
+        xwait = wwait = 0;
         // ---- G2 = G1 W4^T : A from TMEM (G1 bf16 at cols [0,64) and [192,256)), D = cols [64,192), N = 128
         if (!(ok = bwait(&bars[B_G1READY], tp, ctx, 104))) break;
         tc_fence_after();
         K1_TRACE(0, tile, 3);
         for (int st = 0; st < 2 && ok; ++st, ++wst) {
-          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          const uint32_t ws = wst % WSLOTS, wph = (wst / WSLOTS) & 1;
           if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 105))) break;
           tc_fence_after();
 #pragma unroll
@@ -256,7 +300,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         if (!(ok = bwait(&bars[B_G2READY], tp, ctx, 106))) break;
         K1_TRACE(0, tile, 5);
         {
-          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          const uint32_t ws = wst % WSLOTS, wph = (wst / WSLOTS) & 1;
           if (!(ok = bwait(&bars[B_WFULL + ws], wph, ctx, 107))) break;
           tc_fence_after();
 #pragma unroll
@@ -271,6 +315,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         }
         mma_commit(&bars[B_ODONE]);
         K1_TRACE(0, tile, 6);
+        // ---- run-ahead: add-on pass of the next tile's first chunks (acc_A is free once H1 sits in registers)
+        const bool more = tile + 1 < ntiles;
+        const int ra_first = RA / 2;
+        if (more) {
+          if (!(ok = bwait(&bars[B_R1FREE], tp, ctx, 110))) break;
+          tc_fence_after();
+          for (int kc = 0; kc < ra_first && ok; ++kc) ok = wait_x(tile + 1, kc) && issue_pass(tile + 1, kc, 1);
+          if (!ok) break;
+        }
         // ---- pooling: FEpartial^T[d, (slot,p)] = H1^T O ; d halves at cols [0,NPOOL) and [128,128+NPOOL)
         if (!(ok = bwait(&bars[B_OSREADY], tp, ctx, 108))) break;
         K1_TRACE(0, tile, 7);
@@ -290,6 +343,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         mma_commit(&bars[B_OSEMPTY]);
         mma_commit(&bars[B_FEDONE]);
         K1_TRACE(0, tile, 10);
+        if (more)
+          for (int kc = ra_first; kc < RA && ok; ++kc) ok = wait_x(tile + 1, kc) && issue_pass(tile + 1, kc, 1);
       }
     }
   } else if (warp == 1) {
@@ -299,57 +354,70 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       bool ok = true;
       for (int tile = 0; tile < ntiles && ok; ++tile) {
         for (int i = 0; i < stages_per_tile; ++i, ++wst) {
-          const uint32_t ws = wst % 3, wph = (wst / 3) & 1;
+          const uint32_t ws = wst % WSLOTS, wph = (wst / WSLOTS) & 1;
           if (!(ok = bwait(&bars[B_WEMPTY + ws], wph ^ 1, ctx, 201))) break;
           size_t src;
           uint32_t bytes = 32768;
-          if (i < 2 * nkc) src = PL.off_l1 + (size_t)i * 32768;
-          else if (i < 2 * nkc + 2) src = PL.off_w4 + (size_t)(i - 2 * nkc) * 32768;
+          if (i < 2 * nkc) {  // consumption order: W1[0..RA) (issued ahead), W3[0..RA), then (W3[k], W1[k]) for k >= RA
+            const int RA = nkc < 4 ? nkc : 4;
+            int kc, pass;
+            if (i < RA) { kc = i; pass = 1; }
+            else if (i < 2 * RA) { kc = i - RA; pass = 0; }
+            else { kc = RA + ((i - 2 * RA) >> 1); pass = (i - 2 * RA) & 1; }
+            src = PL.off_l1 + (size_t)(2 * kc + pass) * 32768;
+          } else if (i < 2 * nkc + 2) src = PL.off_w4 + (size_t)(i - 2 * nkc) * 32768;
           else { src = PL.off_w5; bytes = 16384; }
+          if (p.dbg_skip & 1) { mbar_arrive(&bars[B_WFULL + ws]); continue; }
           mbar_arrive_expect_tx(&bars[B_WFULL + ws], bytes);
           for (uint32_t o = 0; o < bytes; o += 16384)
             bulk_g2s(w_base + ws * WSLOT_BYTES + o, p.packed + src + o, 16384, &bars[B_WFULL + ws]);
         }
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp >= 2 && warp < 6) {
     // ------------------------------------------------------------------ X producers: NCDHW gather -> MN-major SW128
+    // Four warps, each owning 16 of the 64 channels of a chunk; lane l owns voxels 4l..4l+3 of the tile, so one
+    // warp-wide 8-byte load is a coalesced 256-byte run of one channel row.  global -> registers with an L1-bypassing
+    // load -> st.shared into the swizzled operand layout.  The loads of the next chunk are issued before the stores
+    // of the current one and before waiting for its slot, so HBM latency overlaps both (32 KB in flight per SM).
+    // cp.async.ca was measured at ~50 cycles per instruction here: with >196 KB of smem carved out there is no L1
+    // left for its allocate-on-miss path, and the 16-byte L1-bypassing form needs an alignment NCDHW rows
+    // (392 B pitch) only have for every other channel.
     const int xw = warp - 2;
-    uint32_t chunk = 0;
-    int pending_slot = -1;
+    const uint32_t nchunks = (uint32_t)(ntiles * nkc);
     bool ok = true;
-    for (int tile = 0; tile < ntiles && ok; ++tile) {
+    uint2 va[16], vb[16];
+    auto load_unit = [&](uint32_t g, uint2* v) {
+      const int tile = (int)(g / (uint32_t)nkc), kc = (int)(g - (uint32_t)tile * nkc);
       const int t = tile * TILE_M + 4 * lane;
-      const bool valid = t < ntok;
+      const bool valid = t < ntok && !(p.dbg_skip & 2);
       const int clipl = valid ? t / S : 0;
       const int s = valid ? t - clipl * S : 0;
-      const __nv_bfloat16* src0 = p.feat + ((size_t)(c_begin + clipl) * p.C) * S + s;
-      for (int kc = 0; kc < nkc; ++kc, ++chunk) {
-        const uint32_t xs = chunk & 3, xph = (chunk >> 2) & 1;
-        if (!(ok = bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301))) break;
-        const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-          const int kl = xw * 32 + j;
-          cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, kl, 8192), src0 + (size_t)(kc * 64 + kl) * S, valid ? 8u : 0u);
-        }
-        cp_async_commit();
-        if (pending_slot >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_XFULL + pending_slot]);
-        }
-        pending_slot = (int)xs;
-      }
-    }
-    cp_async_wait<0>();
-    if (ok && pending_slot >= 0) {
+      const __nv_bfloat16* src = p.feat + ((size_t)(c_begin + clipl) * p.C + kc * 64 + xw * 16) * S + s;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = valid ? ldg_nc_na_v2(src + (size_t)j * S) : make_uint2(0u, 0u);
+    };
+    auto store_unit = [&](uint32_t g, const uint2* v) -> bool {
+      const uint32_t xs = g % XSLOTS, xph = (g / XSLOTS) & 1;
+      if (!bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301)) return false;
+      const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) st_shared_v2(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), v[j]);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_XFULL + pending_slot]);
+      if (lane == 0) mbar_arrive(&bars[B_XFULL + xs]);
+      return true;
+    };
+    if (nchunks > 0) load_unit(0, va);
+    for (uint32_t g = 0; g < nchunks && ok; g += 2) {
+      if (g + 1 < nchunks) load_unit(g + 1, vb);
+      if (!(ok = store_unit(g, va))) break;
+      if (g + 1 < nchunks) {
+        if (g + 2 < nchunks) load_unit(g + 2, va);
+        ok = store_unit(g + 1, vb);
+      }
     }
-  } else if (warp == 12) {
+  } else if (warp == 14) {
     // ------------------------------------------------------------------ occurrence column sums (bias term of W2)
     float acc0 = 0.f, acc1 = 0.f;  // p = lane, p = lane + 32
     bool ok = true;
@@ -391,7 +459,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         acc0 = acc1 = 0.f;
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 15) {
     // ------------------------------------------------------------------ occurrence-map store: Os (smem) -> [N][P][S] bf16
     bool ok = true;
     const unsigned char* os = smem + SM_OS;
@@ -417,8 +485,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       if (lane == 0) mbar_arrive(&bars[B_OSEMPTY]);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 4..11
-    const int q = warp & 3, hh = (warp - 4) >> 2;
+    // ------------------------------------------------------------------ epilogue warps 6..13
+    const int q = warp & 3, hh = (warp - EPI_WARP0) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t tl = tbase + lane_base;
     const int tok = q * 32 + lane;
@@ -465,10 +533,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       //      channels 0..127 into cols [0,64); warp hh=1 walks downwards and packs channels 128..255 into [192,256).
       //      Either order only overwrites columns whose fp32 content was already loaded, and it leaves [64,192)
       //      free as one contiguous N=128 accumulator for G2.
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 0);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 0);
       if (!(ok = bwait(&bars[B_L1DONE], tp, ctx, 501))) break;
       tc_fence_after();
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 1);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 1);
       {
         // chunk order: hh=0 ascending 0,1,2,3 -> writes [16c,+16); hh=1 descending 3,2,1,0 -> writes [192+16c,+16)
         uint32_t ra[32], rb[32], pk[16];
@@ -495,17 +563,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G1READY]);
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 2);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 2);
 
       // ---- E2a: first half of H1 -> Hs (overlaps the G2 MMAs)
       h1_convert(0, hp);
       if (!(ok = h1_store(0, hp))) break;
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 3);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 3);
 
       // ---- E3: acc_G2 (cols [64,192)) -> G2 = relu(. + b4) bf16 in place at [64+64hh, +32)
       if (!(ok = bwait(&bars[B_G2DONE], tp, ctx, 503))) break;
       tc_fence_after();
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 4);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 4);
       {
         uint32_t ra[32], rb[32], pk[16];
         const uint32_t col = 64u + 64u * hh;
@@ -522,16 +590,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G2READY]);
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 5);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 5);
 
       // ---- E2b (register part): second half of H1, converted while the O MMAs run
       h1_convert(1, hp);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_R1FREE]);   // acc_A fully consumed: the next tile's add-on pass may start
 
       // ---- E4: acc_O -> O = |.| bf16 -> Os (pooling B operand, slot-in-N layout; other slot and invalid rows zero)
       if (!(ok = bwait(&bars[B_ODONE], tp, ctx, 504))) break;
       tc_fence_after();
       if (!(ok = bwait(&bars[B_OSEMPTY], tp ^ 1, ctx, 505))) break;
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 6);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 6);
       {
         uint32_t r[32];
         tmem_ld_x32(tl + 32 * hh, r);
@@ -556,17 +627,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_OSREADY]);
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 7);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 7);
 
       // ---- E2b (store part)
       if (!(ok = h1_store(1, hp))) break;
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 8);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 8);
 
       // ---- E5: drain FEpartial^T (lane = d) into per-clip register accumulators; finished clips leave as bf16 hi/lo
       //      rows of the K2 operand images
       if (!(ok = bwait(&bars[B_FEDONE], tp, ctx, 506))) break;
       tc_fence_after();
-      if (warp == 4 && lane == 0) K1_TRACE(1, tile, 9);
+      if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 9);
       {
         const int last_tok = min(tile * TILE_M + TILE_M - 1, ntok - 1);
         const int last_clip = last_tok / S;
@@ -591,25 +662,30 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_TMEMFREE]);
-        if (warp == 4 && lane == 0) K1_TRACE(1, tile, 10);
+        if (warp == EPI_WARP0 && lane == 0) K1_TRACE(1, tile, 10);
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
           const bool flush = rep == 0 ? boundary : ends;
           if (!flush) continue;
           const int clip = c_begin + (rep == 0 ? first_clip : last_clip);
+          // K2's A operand is MN-major (row = (clip,p) contiguous, k = d), so this thread's PP values for its d are
+          // PP/8 16-byte chunks per image: rows [rowb, rowb+PP) of k-chunk image d/64, hi at +0 and lo at +64 KB
           const int tile2 = clip / p.cpt;
-          const int rowb = (clip - tile2 * p.cpt) * p.P;
+          const int rowb = (clip - tile2 * p.cpt) * PP;
           uint8_t* img = p.feimg + (size_t)tile2 * FE_TILE_BYTES + (size_t)(d >> 6) * 16384;
 #pragma unroll
-          for (int j = 0; j < PP; ++j) {
-            if (j < p.P) {
-              const float v = facc[j];
-              const __nv_bfloat16 h = __float2bfloat16_rn(v);
-              const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-              const uint32_t off = off_kmajor_sw128(rowb + j, d & 63);
-              *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
-              *reinterpret_cast<__nv_bfloat16*>(img + 65536 + off) = l;
+          for (int c = 0; c < PP / 8; ++c) {
+            uint32_t hi4[4], lo4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float v0 = facc[8 * c + 2 * j], v1 = facc[8 * c + 2 * j + 1];
+              const float h0 = round_bf16(v0), h1 = round_bf16(v1);
+              hi4[j] = pack_bf16x2(h0, h1);
+              lo4[j] = pack_bf16x2(v0 - h0, v1 - h1);
             }
+            const uint32_t off = off_mnmajor_sw128(rowb + 8 * c, d & 63, 8192);
+            *reinterpret_cast<uint4*>(img + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+            *reinterpret_cast<uint4*>(img + 65536 + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
           }
           if (rep == 0) {
 #pragma unroll
@@ -645,7 +721,7 @@ struct K2Params {
   const float* protos; const float* last_layer;
   float* logits; float* sim; float* dist; float* feats;
   const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
-  int N, P, K, cpt, ntiles;
+  int N, P, PP, K, cpt, ntiles;   // PP = padded P (row stride inside a tile), cpt = clips per tile = 128 / PP
   int* err;
 };
 }  // namespace
@@ -724,7 +800,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   } else if (warp == 8) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(128, 256, 1, 0);  // A (pooled vectors) MN-major, B (W2) K-major
       uint32_t u = 0;
       bool ok = true;
       for (int it = 0; it < my_tiles && ok; ++it) {
@@ -739,8 +815,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint64_t bd = make_smem_desc(sb + 32768 + k4 * 32, 16, 1024, SWZ_128B);
-            const uint64_t ah = make_smem_desc(sb + k4 * 32, 16, 1024, SWZ_128B);
-            const uint64_t al = make_smem_desc(sb + 16384 + k4 * 32, 16, 1024, SWZ_128B);
+            const uint64_t ah = make_smem_desc(sb + k4 * 2048, 8192, 1024, SWZ_128B);
+            const uint64_t al = make_smem_desc(sb + 16384 + k4 * 2048, 8192, 1024, SWZ_128B);
             mma_ss(tbase + 256u * buf, ah, bd, idesc, (kc | k4) ? 1u : 0u);
             mma_ss(tbase + 256u * buf, al, bd, idesc, 1u);
           }
@@ -761,9 +837,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       const int clip0 = tile * p.cpt;
       int nclip = p.N - clip0;
       if (nclip > p.cpt) nclip = p.cpt;
-      const int nrows = nclip * p.P;
-      const bool rvalid = r < nrows;
-      const int cl = rvalid ? r / p.P : 0, pp = rvalid ? r - cl * p.P : 0;
+      const int cl_r = r / p.PP, pp_r = r - cl_r * p.PP;          // row = clip-in-tile * PP + prototype
+      const bool rvalid = cl_r < nclip && pp_r < p.P;
+      const int cl = rvalid ? cl_r : 0, pp = rvalid ? pp_r : 0;
       const int n = clip0 + cl;
       const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
       const float* vrow = s_v + pp * 257 + 128 * ch;
@@ -822,7 +898,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       if (tid < nclip * p.K) {
         const int c2 = tid / p.K, k = tid - c2 * p.K;
         float acc = 0.f;
-        for (int qq = 0; qq < p.P; ++qq) acc = fmaf(ssim[c2 * p.P + qq], p.last_layer[(size_t)k * p.P + qq], acc);
+        for (int qq = 0; qq < p.P; ++qq) acc = fmaf(ssim[c2 * p.PP + qq], p.last_layer[(size_t)k * p.P + qq], acc);
         p.logits[(size_t)(clip0 + c2) * p.K + k] = acc;
       }
     }
@@ -903,7 +979,11 @@ bool sm100_supported(const pasn_dims& d) {
 
 size_t sm100_packed_bytes(const pasn_dims& d) { return packed_layout(d.C).total; }
 
-static inline int k2_tiles(const pasn_dims& d) { return ceil_div(d.N, TILE_M / d.P); }
+static inline int k2_ppad(const pasn_dims& d) {
+  const int p8 = (d.P + 7) / 8 * 8;
+  return p8 <= 16 ? 16 : p8 <= 32 ? 32 : p8 <= 40 ? 40 : 48;   // matches the head_tokens_kernel<PP> instantiations
+}
+static inline int k2_tiles(const pasn_dims& d) { return ceil_div(d.N, TILE_M / k2_ppad(d)); }
 
 // workspace: K2 operand images [ntiles2][128 KB] | Osum [N][P] fp32 | err int
 size_t sm100_workspace_bytes(const pasn_dims& d) {
@@ -957,9 +1037,10 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.feimg = feimg; k1.osum = osum;
   k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.nkc = d.C / 64;
   k1.clips_per_cta = ceil_div(d.N, num_sms);
-  k1.cpt = TILE_M / d.P;
+  k1.cpt = TILE_M / k2_ppad(d);
   k1.err = err;
   k1.trace = g_trace;
+  { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
   const int grid1 = ceil_div(d.N, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
   main_kernel_begin(st);
@@ -982,7 +1063,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.global_offset = push ? (long long)push->global_offset : 0;
   k2.best_key = push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
   k2.N = d.N; k2.P = d.P; k2.K = d.K;
-  k2.cpt = TILE_M / d.P;
+  k2.cpt = TILE_M / k2_ppad(d);
+  k2.PP = k2_ppad(d);
   k2.ntiles = k2_tiles(d);
   k2.err = err;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;

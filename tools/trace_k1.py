@@ -10,7 +10,7 @@ sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
 m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
 x = torch.relu(torch.randn((1024, dims.C) + dims.spatial, device="cuda")).bfloat16()
 lib = _lib.load()
-buf = torch.zeros(2 * 16 * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     for _ in range(3):
         m(x)
@@ -18,7 +18,7 @@ with torch.no_grad():
     m(x)
     torch.cuda.synchronize()
     lib.pasn_debug_set_trace(None)
-t = buf.cpu().view(2, 16, 16)
+t = buf.cpu().view(3, 16, 16)
 t0 = int(t[0, 0, 0])
 names_m = ["start", "tmemfree", "L1issued", "g1ready", "G2issued", "g2ready", "Oissued", "osready", "hs0", "hs1", "poolissued"]
 names_e = ["E-start", "l1done", "E1done", "E2a done", "g2done", "E3done", "odone+osempty", "E4done", "E2b done", "fedone", "E5done"]
@@ -27,4 +27,6 @@ for tile in range(12):
         break
     print(f"tile {tile}")
     print("  MMA: " + " ".join(f"{n}={int(t[0, tile, i]) - t0}" for i, n in enumerate(names_m)))
+    print(f"  MMA waits inside L1 (+run-ahead issued before it): x_full {int(t[0, tile, 11])} cyc, w_full {int(t[0, tile, 12])} cyc")
+    print("  x_full wait per chunk kc=0..7:", [int(v) for v in t[2, tile, :8]], " w_full wait per chunk:", [int(v) for v in t[2, tile, 8:16]])
     print("  EPI: " + " ".join(f"{n}={int(t[1, tile, i]) - t0}" for i, n in enumerate(names_e)))
