@@ -296,7 +296,7 @@ def main():
                 model.prototype_vectors.data.copy_(proto0)
                 barrier()
                 e0.record()
-                res = push_resident(model, feats, labels, global_offset=lo, chunk=2048, replace_prototypes=True)
+                res = push_resident(model, feats, labels, global_offset=lo, chunk=8192, replace_prototypes=True)
                 e1.record()
                 barrier()
                 if it > 0:

@@ -93,11 +93,14 @@ def _world(group=None):
     return 0, 1
 
 
-def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_prototypes=True, group=None):
+def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_prototypes=True, group=None, dense=False):
     """Merge keys across ranks, gather winner rows from their owners, overwrite prototypes.
 
     ``fetch_features(global_indices: LongTensor on device) -> backbone feature maps`` for indices in [lo, hi).
-    Returns dict(index, distance, features (P,D), occurrence_maps, logits) -- the last two only for local winners.
+    ``dense=True`` (features resident on the GPU): no host synchronisation at all -- every rank re-runs ``push_forward``
+    on exactly P clips (its winners, or a clamped in-range clip where it is not the owner) and masks by ownership.
+    ``dense=False`` (clips come from a Dataset): only the distinct local winners are fetched.
+    Returns dict(index, distance, features (P,D), side) -- ``side`` carries the winners' occurrence maps / logits.
     """
     import torch.distributed as dist
 
@@ -107,16 +110,26 @@ def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_proto
     merge_keys(best_key, group)
     idx, dmin = decode_keys(best_key)
     mine = (idx >= lo) & (idx < hi)
-    vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
     side = {}
-    if bool(mine.any()):
-        protos = torch.nonzero(mine).flatten()
-        uniq, inv = torch.unique(idx[protos], return_inverse=True)
-        x = fetch_features(uniq)
-        feats, dist_w, occ, logits = model._rt_push_forward_features(x)
-        vec[protos] = feats[inv, protos]
-        side = {"prototypes": protos, "clips": uniq, "inv": inv, "occurrence_maps": occ[inv, protos],
-                "logits": logits[inv], "distance": dist_w[inv, protos]}
+    if dense:
+        ar = torch.arange(P, device=dev)
+        if hi > lo:
+            x = fetch_features(idx.clamp(lo, hi - 1))
+            feats, dist_w, occ, logits = model._rt_push_forward_features(x)
+            vec = torch.where(mine[:, None], feats[ar, ar], torch.zeros((), dtype=torch.float32, device=dev))
+            side = {"owned": mine, "occurrence_maps": occ[ar, ar], "logits": logits, "distance": dist_w[ar, ar]}
+        else:
+            vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
+    else:
+        vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
+        if bool(mine.any()):
+            protos = torch.nonzero(mine).flatten()
+            uniq, inv = torch.unique(idx[protos], return_inverse=True)
+            x = fetch_features(uniq)
+            feats, dist_w, occ, logits = model._rt_push_forward_features(x)
+            vec[protos] = feats[inv, protos]
+            side = {"prototypes": protos, "clips": uniq, "inv": inv, "occurrence_maps": occ[inv, protos],
+                    "logits": logits[inv], "distance": dist_w[inv, protos]}
     rank, world = _world(group)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
@@ -131,7 +144,7 @@ def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_proto
 
 
 def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_offset: int = 0, n_total: Optional[int] = None,
-                  chunk: int = 2048, class_specific=True, abstain_class=True, replace_prototypes=True, group=None):
+                  chunk: int = 8192, class_specific=True, abstain_class=True, replace_prototypes=True, group=None):
     """Push over backbone feature maps already resident on this rank's GPU (``features`` [n_local,C,*spatial],
     ``labels`` int64 [n_local]); ``global_offset`` = global index of local clip 0.  This is the path bench.py times."""
     dev = features.device
@@ -146,7 +159,7 @@ def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_of
     def fetch(gidx):
         return features.index_select(0, gidx - lo)
 
-    return finish_push(model, key, fetch, lo, hi, replace_prototypes, group)
+    return finish_push(model, key, fetch, lo, hi, replace_prototypes, group, dense=True)
 
 
 def push_prototypes(
