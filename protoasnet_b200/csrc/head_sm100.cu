@@ -23,18 +23,15 @@
 //                          cosine -> (.+1)/2 -> logits -> 1-s -> packed argmin keys chain (cf. proto_stage.cu).
 #include <cstdlib>
 
-#include "common.cuh"
-#include "sm100_prims.cuh"
+#include "head_sm100_shared.cuh"
 
 namespace pasn {
 using namespace sm100;
 
+using namespace k1;
+
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int DD = 256;            // prototype depth D handled by this kernel
-constexpr int DH = DD / 2;         // occurrence hidden width
-constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
 constexpr int XSLOTS = 4;
 #ifndef PASN_WSLOTS
 #define PASN_WSLOTS 3
@@ -44,8 +41,6 @@ constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768, HS_BYTES = 32768;
 constexpr int K1_WARPS = 16;
 constexpr int EPI_WARP0 = 6;   // warps 6..13: epilogue (TMEM quadrant = warp % 4), 14: Osum, 15: occurrence-map store
 constexpr int K1_THREADS = K1_WARPS * 32;
-constexpr uint32_t FE_TILE_BYTES = 131072;  // K2 operand images of one 128-row tile: hi 64 KB | lo 64 KB
-
 // shared-memory map of K1 (offsets from a 1024-byte aligned base)
 constexpr uint32_t SM_X = 0;
 constexpr uint32_t SM_W = SM_X + XSLOTS * XSLOT_BYTES;            // 65536
@@ -62,78 +57,6 @@ enum {
   B_OSREADY, B_OSEMPTY, B_HSREADY, B_HSEMPTY, B_FEDONE, B_TMEMFREE, B_R1FREE, B_COUNT
 };
 static_assert(B_COUNT <= 32, "barrier table");
-
-// packed weight buffer (bf16 stage images + fp32 biases), see pack_weights_kernel
-struct PackedLayout {
-  size_t off_l1, off_w4, off_w5, off_bias, off_w2, off_b2, total;
-};
-__host__ __device__ inline PackedLayout packed_layout(int C) {
-  PackedLayout L;
-  const int nkc = C / 64;
-  L.off_l1 = 0;
-  L.off_w4 = (size_t)2 * nkc * 32768;
-  L.off_w5 = L.off_w4 + 65536;
-  L.off_bias = L.off_w5 + 16384;
-  L.off_w2 = (L.off_bias + (DD + DD + DH) * 4 + 1023) / 1024 * 1024;
-  L.off_b2 = L.off_w2 + 4 * 32768;
-  L.total = L.off_b2 + DD * 4;
-  return L;
-}
-
-struct K1Params {
-  const __nv_bfloat16* feat;   // [N][C][S]
-  const uint8_t* packed;
-  __nv_bfloat16* occ;          // [N][P][S] or null
-  uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile
-  float* osum;                 // [N][P]
-  int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / PP
-  int* err;
-  long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
-  int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X
-};
-
-struct Ctx {
-  int* err;
-  volatile int* abort_s;
-};
-
-// bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug
-__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*c.abort_s) return false;
-    if (clock64() - t0 > 4000000000ll) {
-      *c.abort_s = 1;
-      atomicCAS(c.err, 0, code);
-      return false;
-    }
-  }
-  return true;
-}
-
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// 32 fp32 accumulator columns + bias -> ReLU -> 16 packed bf16x2 (bias: 32 floats in smem, 16-byte aligned)
-__device__ __forceinline__ void bias_relu_pack(const uint32_t (&r)[32], const float* bias, uint32_t* pk) {
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j4);
-    pk[2 * j4] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 0]) + b.x, __uint_as_float(r[4 * j4 + 1]) + b.y);
-    pk[2 * j4 + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 2]) + b.z, __uint_as_float(r[4 * j4 + 3]) + b.w);
-  }
-}
-
-#define K1_TRACE(role, tile, slot)                                                            \
-  do {                                                                                        \
-    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 16)                                 \
-      p.trace[((role) * 16 + (tile)) * 16 + (slot)] = clock64();                              \
-  } while (0)
 
 }  // namespace
 
@@ -1043,9 +966,13 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
   const int grid1 = ceil_div(d.N, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
+  // The CTA-pair (cta_group::2) variant is correct but measured slower (237 us vs 170 us at cfg 3, N = 1024: its
+  // weight relay and cross-CTA hand-offs cost more than the halved weight ingest saves) -- opt-in for experiments.
+  static const bool use_pair = [] { const char* e = getenv("PASN_K1_PAIR"); return e && atoi(e) != 0; }();
   main_kernel_begin(st);
   int rc;
-  if (ppad <= 16) rc = launch_k1<16>(k1, grid1, st);
+  if (use_pair) rc = launch_k1_pair(k1, ppad, st);
+  else if (ppad <= 16) rc = launch_k1<16>(k1, grid1, st);
   else if (ppad <= 32) rc = launch_k1<32>(k1, grid1, st);
   else if (ppad <= 40) rc = launch_k1<40>(k1, grid1, st);
   else rc = launch_k1<48>(k1, grid1, st);

@@ -1,0 +1,95 @@
+// Definitions shared by the single-CTA and CTA-pair variants of the fused token kernel (head_sm100.cu,
+// head_sm100_pair.cu): tile constants, packed-weight layout, kernel parameters, bounded waits, epilogue helpers.
+#pragma once
+#include "common.cuh"
+#include "sm100_prims.cuh"
+
+namespace pasn {
+namespace k1 {
+using namespace sm100;
+
+constexpr int TILE_M = 128;
+constexpr int DD = 256;            // prototype depth D handled by this kernel
+constexpr int DH = DD / 2;         // occurrence hidden width
+constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
+constexpr uint32_t FE_TILE_BYTES = 131072;  // K2 operand images of one 128-row tile: hi 64 KB | lo 64 KB
+
+// packed weight buffer (bf16 stage images + fp32 biases), see pack_weights_kernel
+struct PackedLayout {
+  size_t off_l1, off_w4, off_w5, off_bias, off_w2, off_b2, total;
+};
+__host__ __device__ inline PackedLayout packed_layout(int C) {
+  PackedLayout L;
+  const int nkc = C / 64;
+  L.off_l1 = 0;
+  L.off_w4 = (size_t)2 * nkc * 32768;
+  L.off_w5 = L.off_w4 + 65536;
+  L.off_bias = L.off_w5 + 16384;
+  L.off_w2 = (L.off_bias + (DD + DD + DH) * 4 + 1023) / 1024 * 1024;
+  L.off_b2 = L.off_w2 + 4 * 32768;
+  L.total = L.off_b2 + DD * 4;
+  return L;
+}
+
+struct K1Params {
+  const __nv_bfloat16* feat;   // [N][C][S]
+  const uint8_t* packed;
+  __nv_bfloat16* occ;          // [N][P][S] or null
+  uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile
+  float* osum;                 // [N][P]
+  int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / PP
+  int* err;
+  long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
+  int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X
+};
+
+struct Ctx {
+  int* err;
+  volatile int* abort_s;
+};
+
+// bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug
+__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*c.abort_s) return false;
+    if (clock64() - t0 > 4000000000ll) {
+      *c.abort_s = 1;
+      atomicCAS(c.err, 0, code);
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 32 fp32 accumulator columns + bias -> ReLU -> 16 packed bf16x2 (bias: 32 floats in smem, 16-byte aligned)
+__device__ __forceinline__ void bias_relu_pack(const uint32_t (&r)[32], const float* bias, uint32_t* pk) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j4);
+    pk[2 * j4] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 0]) + b.x, __uint_as_float(r[4 * j4 + 1]) + b.y);
+    pk[2 * j4 + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * j4 + 2]) + b.z, __uint_as_float(r[4 * j4 + 3]) + b.w);
+  }
+}
+
+#define K1_TRACE(role, tile, slot)                                                            \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 16)                                 \
+      p.trace[((role) * 16 + (tile)) * 16 + (slot)] = clock64();                              \
+  } while (0)
+
+
+}  // namespace k1
+
+// pair variant (head_sm100_pair.cu)
+int launch_k1_pair(const k1::K1Params& k1p, int ppad, cudaStream_t st);
+
+}  // namespace pasn
