@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();   // K2 may start launching (its CTAs only fit on an SM once one of ours has exited)
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t x_base = smem_u32(smem + SM_X), w_base = smem_u32(smem + SM_W);
   const uint32_t hs_base = smem_u32(smem + SM_HS), os_base = smem_u32(smem + SM_OS);
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   if (warp == 9) {
     // ---------------------------------------------------------------- loader
     if (lane == 0) {
+      griddep_wait();   // the pooled-vector images are written by the token kernel
       uint32_t u = 0;
       bool ok = true;
       for (int it = 0; it < my_tiles && ok; ++it) {
@@ -753,6 +755,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     const int q = warp & 3, ch = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane;
+    griddep_wait();   // Osum is written by the token kernel
     bool ok = true;
     for (int it = 0; it < my_tiles && ok; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -995,7 +998,15 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.ntiles = k2_tiles(d);
   k2.err = err;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;
-  proto_w2_kernel<<<grid2, K2_THREADS, K2_SMEM, st>>>(k2);
+  {  // programmatic dependent launch: K2's prologue (TMEM, barriers, norms, the resident W2 images) overlaps K1's tail
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid2); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = K2_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, proto_w2_kernel, k2) != cudaSuccess) return PASN_ERR_CUDA;
+  }
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;

@@ -101,6 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KP_THREADS, 1) head_
   __syncthreads();
   cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / multicast commit
   tc_fence_after();
+  griddep_launch_dependents();   // K2 may start launching (its CTAs only fit on an SM once one of ours has exited)
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t x_base = smem_u32(smem + SM_X), w_base = smem_u32(smem + SM_W);
   const uint32_t hs_base = smem_u32(smem + SM_HS), os_base = smem_u32(smem + SM_OS);

@@ -73,6 +73,10 @@ __device__ __forceinline__ uint2 ldg_nc_na_v2(const void* p) {
 __device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint2 v) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
 }
+// programmatic dependent launch: wait until the preceding grid in the stream has completed and flushed its writes /
+// allow the following grid to start launching
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // arrive on `bar` (without bumping its pending count) once all cp.async issued so far by this thread have landed
