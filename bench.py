@@ -292,21 +292,23 @@ def main():
         proto0 = model.prototype_vectors.data.clone()
         times, idx_ref = [], None
         with torch.no_grad():
-            for it in range(1 + 3):
+            n_warm, n_timed = 2, 5   # NCCL / allocator first-use effects last into the second push
+            for it in range(n_warm + n_timed):
                 model.prototype_vectors.data.copy_(proto0)
                 barrier()
                 e0.record()
                 res = push_resident(model, feats, labels, global_offset=lo, chunk=8192, replace_prototypes=True)
                 e1.record()
                 barrier()
-                if it > 0:
+                if it >= n_warm:
                     times.append(e0.elapsed_time(e1))
                 if idx_ref is None:
                     idx_ref = res["index"].clone()
                 assert torch.equal(idx_ref, res["index"])
-        push_ms = max_over_ranks(float(np.mean(times)))
+        push_ms = max_over_ranks(float(np.median(times)))
         f_push = n_total * (flops_clip - 0)  # same head FLOPs per clip (no occurrence-map store)
         push = {"seconds_per_50k": push_ms * 1e-3 * (50000 / n_total), "clips": n_total, "ms": push_ms, "n_gpus": world,
+                "ms_runs_rank0": [round(t, 3) for t in times],
                 "clips_per_sec": n_total / (push_ms * 1e-3), "scaling": "strong",
                 "tensor_frac_of_sustained": f_push / (push_ms * 1e-3) / 1e12 / (world * peaks["bf16_tflops_sustained"]),
                 "winners_sample": idx_ref[:8].tolist(), "collectives_per_push": 2 if world > 1 else 0}

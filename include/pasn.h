@@ -94,7 +94,9 @@ typedef struct {
   const int32_t* proto_class; /* [P] class a prototype is restricted to, or -1 for unrestricted        */
                               /*     (abstention prototypes, push_abs_revision.py:231-237)             */
   int64_t global_offset;      /* global index of clip 0 of this call in the unshuffled training set    */
-  uint64_t* best_key;         /* [P] in/out running minimum of (orderable(dist) << 32 | global index)  */
+  uint64_t* best_key;         /* [P] in/out running minimum of (orderable(dist) << 32 | global index), stored    */
+                              /*     with the top bit flipped: signed int64 order == key order, so one            */
+                              /*     all-reduce(MIN, int64) merges ranks; INT64_MAX = no candidate yet            */
 } pasn_push_args;
 
 int pasn_abi_version(void);
@@ -133,6 +135,11 @@ int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dim
 int pasn_push_init(uint64_t* best_key, int32_t P, void* stream);          /* best_key[:] = +inf / no index */
 int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* index[p] = winner or -1       */
                      float* distance, void* stream);                      /* distance[p] fp32 (inf if none)*/
+/* decode + ownership of range [lo,hi): index, distance, clamped local index (index - lo), own flag, valid flag */
+int pasn_push_select(const uint64_t* best_key, int32_t P, int64_t lo, int64_t hi, int64_t* index, float* distance,
+                     int64_t* local_index, int32_t* own, int32_t* valid, void* stream);
+/* vec[p,:] = own[p] ? feats[p,p,:] : 0, feats = features_extracted [P,P,D] of the P re-fetched winner clips */
+int pasn_push_collect(const float* feats, const int32_t* own, float* vec, int32_t P, int32_t D, void* stream);
 /* prototype_vectors[p,:] = vec[p,:] where valid[p] != 0 (else unchanged) */
 int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_t* valid, int32_t P, int32_t D,
                                void* stream);

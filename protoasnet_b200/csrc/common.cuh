@@ -46,6 +46,13 @@ __host__ __device__ __forceinline__ unsigned long long pack_key(float dist, uint
   return ((unsigned long long)f32_orderable(dist) << 32) | (unsigned long long)gidx;
 }
 #define PASN_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+// Keys are kept as unsigned (orderable(dist) << 32 | index) inside a kernel; in global memory (pasn_push_args.best_key)
+// the top bit is flipped so that SIGNED 64-bit order equals the unsigned key order -- an NCCL all-reduce(MIN) over
+// int64 then merges ranks directly.  "No candidate" is INT64_MAX.
+#define PASN_KEY_SIGN 0x8000000000000000ull
+__device__ __forceinline__ void key_atomic_min_global(unsigned long long* best_key_signed, unsigned long long key_u) {
+  atomicMin(reinterpret_cast<long long*>(best_key_signed), (long long)(key_u ^ PASN_KEY_SIGN));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

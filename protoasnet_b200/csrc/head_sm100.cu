@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   }
   tc_fence_before();
   __syncthreads();
-  if (p.best_key && tid < p.P && s_key[tid] != PASN_KEY_NONE) atomicMin(&p.best_key[tid], s_key[tid]);
+  if (p.best_key && tid < p.P && s_key[tid] != PASN_KEY_NONE) key_atomic_min_global(&p.best_key[tid], s_key[tid]);
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 

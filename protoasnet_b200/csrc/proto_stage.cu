@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(PS_THREADS) proto_stage_kernel(
   }
   if (do_push)
     for (int p = threadIdx.x; p < P; p += PS_THREADS)
-      if (s_key[p] != PASN_KEY_NONE) atomicMin(&best_key[p], s_key[p]);
+      if (s_key[p] != PASN_KEY_NONE) key_atomic_min_global(&best_key[p], s_key[p]);
 }
 
 int launch_proto_stage(const float* feats, const float* protos, const float* last_layer, int N, int P, int D, int K,
@@ -102,19 +102,36 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
 // ---------------------------------------------------------------------------------------------
 __global__ void push_init_kernel(unsigned long long* k, int P) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) k[i] = PASN_KEY_NONE;
+  if (i < P) k[i] = PASN_KEY_NONE ^ PASN_KEY_SIGN;   // INT64_MAX in the signed-order global format
 }
-__global__ void push_decode_kernel(const unsigned long long* k, int P, int64_t* index, float* distance) {
+// decode + ownership in one launch: index / distance of the winner, whether this rank's range [lo, hi) owns it, and the
+// (clamped) local index to re-fetch it from
+__global__ void push_select_kernel(const unsigned long long* k, int P, long long lo, long long hi, int64_t* index,
+                                   float* distance, int64_t* local_index, int32_t* own, int32_t* valid) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  unsigned long long key = k[i];
-  if (key == PASN_KEY_NONE) {
-    index[i] = -1;
-    if (distance) distance[i] = __int_as_float(0x7f800000);
-  } else {
-    index[i] = (int64_t)(key & 0xFFFFFFFFull);
-    if (distance) distance[i] = f32_from_orderable((uint32_t)(key >> 32));
+  const unsigned long long key = k[i] ^ PASN_KEY_SIGN;
+  long long idx = -1;
+  float d = __int_as_float(0x7f800000);
+  if (key != PASN_KEY_NONE) {
+    idx = (long long)(key & 0xFFFFFFFFull);
+    d = f32_from_orderable((uint32_t)(key >> 32));
   }
+  index[i] = idx;
+  if (distance) distance[i] = d;
+  if (valid) valid[i] = idx >= 0;
+  if (own) own[i] = idx >= lo && idx < hi;
+  if (local_index) {
+    long long l = idx < lo ? lo : (idx >= hi ? hi - 1 : idx);
+    local_index[i] = hi > lo ? l - lo : 0;
+  }
+}
+// vec[p,:] = own[p] ? feats[p,p,:] : 0   (feats = push_forward output over the P re-fetched winner clips)
+__global__ void push_collect_kernel(const float* feats, const int32_t* own, float* vec, int P, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)P * D) return;
+  const int p = (int)(i / D), d = (int)(i - (long long)p * D);
+  vec[i] = own[p] ? feats[((size_t)p * P + p) * D + d] : 0.f;
 }
 __global__ void push_write_kernel(float* protos, const float* vec, const int32_t* valid, int P, int D) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,8 +152,25 @@ extern "C" int pasn_push_init(uint64_t* best_key, int32_t P, void* stream) {
 }
 extern "C" int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, float* distance, void* stream) {
   if (!best_key || !index || P <= 0) return PASN_ERR_INVALID;
-  push_decode_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const unsigned long long*>(best_key), P, index, distance);
+  push_select_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(best_key), P, 0, 0, index, distance, nullptr, nullptr, nullptr);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+extern "C" int pasn_push_select(const uint64_t* best_key, int32_t P, int64_t lo, int64_t hi, int64_t* index,
+                                float* distance, int64_t* local_index, int32_t* own, int32_t* valid, void* stream) {
+  if (!best_key || !index || P <= 0 || hi < lo) return PASN_ERR_INVALID;
+  push_select_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(best_key), P, lo, hi, index, distance, local_index, own, valid);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+extern "C" int pasn_push_collect(const float* feats, const int32_t* own, float* vec, int32_t P, int32_t D, void* stream) {
+  if (!feats || !own || !vec || P <= 0 || D <= 0) return PASN_ERR_INVALID;
+  long long n = (long long)P * D;
+  push_collect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(feats, own, vec, P, D);
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;

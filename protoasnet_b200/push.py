@@ -56,25 +56,28 @@ def new_best_key(P: int, device) -> torch.Tensor:
 
 
 def merge_keys(best_key: torch.Tensor, group=None) -> torch.Tensor:
-    """All-reduce(MIN) of uint64 keys stored in an int64 tensor (sign-bit flip keeps unsigned order)."""
+    """All-reduce(MIN) of the packed keys.  They are stored with the top bit flipped (include/pasn.h), so the signed
+    int64 order NCCL / gloo reduce with is the key order: lowest distance first, ties to the lowest global index."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        flipped = best_key ^ _SIGN
-        dist.all_reduce(flipped, op=dist.ReduceOp.MIN, group=group)
-        best_key.copy_(flipped ^ _SIGN)
+        dist.all_reduce(best_key, op=dist.ReduceOp.MIN, group=group)
     return best_key
+
+
+_KEY_NONE = (1 << 63) - 1   # INT64_MAX: no candidate
 
 
 def decode_keys(best_key: torch.Tensor):
     """-> (index int64 [P] (-1 = no candidate), distance fp32 [P])."""
     if not best_key.is_cuda:  # host-side bookkeeping only (gloo tests of the merge logic); no head compute here
-        none = best_key == -1
-        o = (best_key >> 32) & 0xFFFFFFFF
+        none = best_key == _KEY_NONE
+        ku = best_key ^ _SIGN                      # back to the unsigned key bit pattern (held in an int64)
+        o = (ku >> 32) & 0xFFFFFFFF
         u = torch.where((o & 0x80000000) != 0, o & 0x7FFFFFFF, (~o) & 0xFFFFFFFF)
         u = torch.where(u >= (1 << 31), u - (1 << 32), u).to(torch.int32)
         d = torch.where(none, torch.full_like(u, 0x7F800000), u).view(torch.float32)
-        return torch.where(none, torch.full_like(best_key, -1), best_key & 0xFFFFFFFF), d
+        return torch.where(none, torch.full_like(best_key, -1), ku & 0xFFFFFFFF), d
     lib = _lib.load()
     P = best_key.numel()
     idx = torch.empty(P, dtype=torch.int64, device=best_key.device)
@@ -108,19 +111,30 @@ def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_proto
     dev = best_key.device
     P, D = model.num_prototypes, model.prototype_shape[1]
     merge_keys(best_key, group)
-    idx, dmin = decode_keys(best_key)
-    mine = (idx >= lo) & (idx < hi)
     side = {}
     if dense:
-        ar = torch.arange(P, device=dev)
-        if hi > lo:
-            x = fetch_features(idx.clamp(lo, hi - 1))
-            feats, dist_w, occ, logits = model._rt_push_forward_features(x)
-            vec = torch.where(mine[:, None], feats[ar, ar], torch.zeros((), dtype=torch.float32, device=dev))
-            side = {"owned": mine, "occurrence_maps": occ[ar, ar], "logits": logits, "distance": dist_w[ar, ar]}
-        else:
-            vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
+        # one launch decodes the keys and derives ownership / clamped local indices; one launch collects the rows
+        idx = torch.empty(P, dtype=torch.int64, device=dev)
+        dmin = torch.empty(P, dtype=torch.float32, device=dev)
+        local = torch.empty(P, dtype=torch.int64, device=dev)
+        own = torch.empty(P, dtype=torch.int32, device=dev)
+        valid = torch.empty(P, dtype=torch.int32, device=dev)
+        vec = torch.empty((P, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.pasn_push_select(best_key.data_ptr(), P, lo, hi, idx.data_ptr(), dmin.data_ptr(),
+                                            local.data_ptr(), own.data_ptr(), valid.data_ptr(), st), "pasn_push_select")
+            if hi > lo:
+                feats, dist_w, occ, logits = model._rt_push_forward_features(fetch_features(local + lo))
+                _lib.check(lib.pasn_push_collect(feats.data_ptr(), own.data_ptr(), vec.data_ptr(), P, D, st),
+                           "pasn_push_collect")
+                side = {"owned": own, "occurrence_maps": occ, "logits": logits, "distance": dist_w}  # row p <-> prototype p
+            else:
+                vec.zero_()
     else:
+        idx, dmin = decode_keys(best_key)
+        mine = (idx >= lo) & (idx < hi)
+        valid = (idx >= 0).to(torch.int32)
         vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
         if bool(mine.any()):
             protos = torch.nonzero(mine).flatten()
@@ -133,7 +147,6 @@ def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_proto
     rank, world = _world(group)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-    valid = (idx >= 0).to(torch.int32)
     if replace_prototypes:
         pv = model.prototype_vectors.data
         with torch.cuda.device(dev):

@@ -17,7 +17,11 @@ def _f32_orderable(d):
 
 
 def _pack(d, idx):
-    return ((_f32_orderable(d) << np.uint64(32)) | np.asarray(idx, dtype=np.uint64)).astype(np.uint64)
+    """global key format of include/pasn.h: (orderable(dist) << 32 | index) with the top bit flipped (signed order)"""
+    return (((_f32_orderable(d) << np.uint64(32)) | np.asarray(idx, dtype=np.uint64)) ^ np.uint64(1 << 63)).astype(np.uint64)
+
+
+_NONE = np.uint64((1 << 63) - 1)
 
 
 def _worker(rank, world, port, n_total, P, D, ret):
@@ -29,10 +33,11 @@ def _worker(rank, world, port, n_total, P, D, ret):
         dmat[3, 1] = dmat[40, 1] = dmat[:, 1].min() - np.float32(0.5)          # exact tie across ranks
         feats = g.standard_normal((n_total, P, D), dtype=np.float32)
         lo, hi = synth.shard_range(n_total, rank, world)
-        key = np.full(P, np.uint64(0xFFFFFFFFFFFFFFFF))
+        key = np.full(P, _NONE).view(np.int64)
         for n in range(lo, hi):
-            key = np.minimum(key, _pack(dmat[n], np.full(P, n)))
-        key[2] = np.uint64(0xFFFFFFFFFFFFFFFF) if True else key[2]             # prototype 2: no candidate anywhere
+            key = np.minimum(key, _pack(dmat[n], np.full(P, n)).view(np.int64))   # signed order == key order
+        key = key.view(np.uint64).copy()
+        key[2] = _NONE                                                         # prototype 2: no candidate anywhere
         kt = torch.from_numpy(key.view(np.int64).copy())
         pushmod.merge_keys(kt)
         idx, dmin = pushmod.decode_keys(kt)
@@ -75,5 +80,5 @@ def test_decode_keys_host_matches_packing():
     k = _pack(d, [5, 6, 7, 8])
     idx, dd = pushmod.decode_keys(torch.from_numpy(k.view(np.int64).copy()))
     assert idx.tolist() == [5, 6, 7, 8] and np.array_equal(dd.numpy(), d)
-    order = np.argsort(k)
-    assert order.tolist() == [1, 2, 0, 3]                       # unsigned key order == fp32 order
+    order = np.argsort(k.view(np.int64))
+    assert order.tolist() == [1, 2, 0, 3]                       # signed key order == fp32 order

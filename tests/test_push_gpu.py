@@ -118,8 +118,7 @@ def test_push_full_size_properties():
                 j = min(i + 1000, hi)
                 m.push_scan(x[i:j], y[i:j], pc, i, k, backbone=False)
             keys.append(k)
-        merged = torch.stack(keys).view(torch.int64)
-        merged = ((merged ^ pushmod._SIGN).min(dim=0).values) ^ pushmod._SIGN
+        merged = torch.stack(keys).min(dim=0).values      # signed int64 order == key order (include/pasn.h)
         # winners are identical for any sharding; the fp32 distance may differ in its last bits because the fused
         # kernel's pooling order depends on where a clip falls in the 128-voxel tiling of its batch
         idx_m, dist_m = pushmod.decode_keys(merged)
