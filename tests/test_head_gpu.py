@@ -146,3 +146,67 @@ def test_full_size_properties_cfg3(dtype):
     assert_close(d[idx], rd.numpy(), tol, "dist vs oracle")
     assert_close(logits[idx], rl.numpy(), tol, "logits vs oracle")
     assert_close(f[idx], rf.numpy(), tol if not bf else 4e-3, "feats vs oracle")
+
+
+# ------------------------------------------------------------------------------------------------
+# fused tcgen05 path: shape sweep (every template instantiation, ragged tails, CTA / tile boundaries)
+# ------------------------------------------------------------------------------------------------
+TC_SHAPES = [
+    # C, P, K, spatial (S % 4 == 0, S >= 128), n
+    (64, 8, 4, (2, 8, 8), 3),        # smallest channel count, PP=16 instantiation, S = 128 (tile == clip)
+    (128, 12, 3, (1, 10, 14), 5),    # S = 140: every tile straddles clips; P not a multiple of 8
+    (256, 24, 4, (8, 14, 14), 2),    # cfg-1 feature map, PP=32
+    (512, 40, 4, (4, 7, 7), 9),      # cfg-3, PP=40
+    (512, 48, 4, (4, 7, 7), 4),      # PP=48
+    (1024, 40, 8, (3, 8, 8), 2),     # 16 channel chunks; S = 192
+    (512, 40, 4, (4, 7, 7), 149),    # one more clip than SMs: uneven clip ranges per CTA
+    (512, 40, 4, (4, 7, 7), 301),    # 3 clips per CTA with a short last CTA
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=[str(s) for s in TC_SHAPES])
+def test_tcgen05_path_shape_sweep(shape):
+    C, P, K, spatial, n = shape
+    dims = synth.HeadDims(C, 256, P, K, spatial)
+    sd = synth.make_head_params(dims, seed=41, bias_scale=0.05, last_layer_noise=0.1, bf16_round=True)
+    x = synth.make_features(dims, n, seed=23, bf16_round=True)
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)      # errors out if the fused path cannot take the shape
+    mg = build_model(dims, sd, path=_lib.PASN_PATH_GENERIC)
+    xg = torch.from_numpy(x).cuda().bfloat16()
+    out = _run_all(m, xg)
+    ref = _run_all(mg, xg)                                      # generic CUDA path: fp32 math on the same bf16 inputs
+    nref = min(n, 4)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x[:nref]), ho.to_torch_sd(sd))
+    assert_close(out["similarity"][:nref], (1 - rd).numpy(), BF16_RTOL, "similarity vs oracle")
+    assert_close(out["logits"][:nref], rl.numpy(), BF16_RTOL, "logits vs oracle")
+    assert_close(out["similarity"], ref["similarity"].cpu().numpy(), BF16_RTOL, "similarity vs generic")
+    assert_close(out["logits"], ref["logits"].cpu().numpy(), BF16_RTOL, "logits vs generic")
+    assert_close(out["features_extracted"], ref["features_extracted"].cpu().numpy(), 4e-3, "features vs generic")
+    assert_close(out["occurrence_map"], ref["occurrence_map"].float().cpu().numpy(), 2e-2, "occ vs generic", atol_frac=1e-2)
+    assert torch.equal(out["distance"], 1 - out["similarity"])
+
+
+def test_tcgen05_path_refuses_unsupported_shapes():
+    dims = synth.CONFIGS["cfg2_image"]                            # D = 512, S = 49: generic path only
+    m = build_model(dims, synth.make_head_params(dims, seed=1, bf16_round=True), path=_lib.PASN_PATH_TCGEN05)
+    x = torch.zeros((2, dims.C) + dims.spatial, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad(), pytest.raises(_lib.PasnError):
+        m(x)
+    m.kernel_path = _lib.PASN_PATH_AUTO                           # AUTO silently picks the generic CUDA path
+    with torch.no_grad():
+        logits, sim, occ = m(x)
+    assert logits.shape == (2, dims.K)
+
+
+def test_cfg2_image_bf16_generic_matches_oracle():
+    dims = synth.CONFIGS["cfg2_image"]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    x = synth.make_features(dims, 5, seed=0, bf16_round=True)
+    m = build_model(dims, sd)
+    out = _run_all(m, torch.from_numpy(x).cuda().bfloat16())
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x), ho.to_torch_sd(sd))
+    assert_close(out["similarity"], (1 - rd).numpy(), BF16_RTOL, "similarity")
+    assert_close(out["logits"], rl.numpy(), BF16_RTOL, "logits")
+    assert_close(out["features_extracted"], rf.numpy(), BF16_RTOL, "features (fp32 math on bf16 inputs)")
