@@ -330,6 +330,10 @@ def main():
         achieved_tf = BATCH * flops_clip / (main_ms_avg * 1e-3) / 1e12
         timed_s = ms_step * args.steps * 1e-3
         peak = peaks["bf16_tflops"] if timed_s < 1.0 else peaks["bf16_tflops_sustained"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if tc and os.path.exists(tpath):   # dram__bytes_read+write of the dominant kernel from the committed ncu capture
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
             "metric": "head_fwd_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -339,7 +343,8 @@ def main():
                        "batch_per_gpu": BATCH, "layout": "NCDHW", "kernel_path": "tcgen05" if tc else "generic",
                        "l2": "input 205 MB per step > 126 MB L2: re-read from HBM every step"},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak, "traffic": None,
+                         "frac": achieved_tf / peak, "traffic": traffic,
+                         "traffic_algorithmic_bytes": BATCH * bytes_clip,
                          "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}), "
                                         + ("burst" if timed_s < 1.0 else "sustained"),
                          "frac_of_sustained": achieved_tf / peaks["bf16_tflops_sustained"],
