@@ -332,13 +332,55 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
       if (lane == 0) mbar_arrive(&bars[B_XFULL + xs]);
       return true;
     };
-    if (nchunks > 0) load_unit(0, va);
-    for (uint32_t g = 0; g < nchunks && ok; g += 2) {
-      if (g + 1 < nchunks) load_unit(g + 1, vb);
-      if (!(ok = store_unit(g, va))) break;
-      if (g + 1 < nchunks) {
-        if (g + 2 < nchunks) load_unit(g + 2, va);
-        ok = store_unit(g + 1, vb);
+    if (!p.f32_in) {
+      if (nchunks > 0) load_unit(0, va);
+      for (uint32_t g = 0; g < nchunks && ok; g += 2) {
+        if (g + 1 < nchunks) load_unit(g + 1, vb);
+        if (!(ok = store_unit(g, va))) break;
+        if (g + 1 < nchunks) {
+          if (g + 2 < nchunks) load_unit(g + 2, va);
+          ok = store_unit(g + 1, vb);
+        }
+      }
+    } else {
+      // fp32 feature maps ("bf16 compute" mode, opt-in): 16-byte loads of 4 voxels, rounded to bf16 on the way into
+      // smem.  Units are 8 channel rows (u = 2*chunk + half) so the raw loads of the next unit fit in registers.
+      float4* qa = reinterpret_cast<float4*>(va);   // 8 x float4 alias the 16 x uint2 buffers
+      float4* qb = reinterpret_cast<float4*>(vb);
+      const uint32_t nunits = 2 * nchunks;
+      auto load32 = [&](uint32_t u, float4* q) {
+        const uint32_t g = u >> 1, h = u & 1;
+        const int tile = (int)(g / (uint32_t)nkc), kc = (int)(g - (uint32_t)tile * nkc);
+        const int t = tile * TILE_M + 4 * lane;
+        const bool valid = t < ntok;
+        const int clipl = valid ? t / S : 0;
+        const int s = valid ? t - clipl * S : 0;
+        const float* src = p.feat32 + ((size_t)(c_begin + clipl) * p.C + kc * 64 + xw * 16 + 8 * h) * S + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = valid ? ldg_nc_na_v4f(src + (size_t)j * S) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto store32 = [&](uint32_t u, const float4* q) -> bool {
+        const uint32_t g = u >> 1, h = u & 1;
+        const uint32_t xs = g % XSLOTS, xph = (g / XSLOTS) & 1;
+        if (h == 0 && !bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301)) return false;
+        const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v2(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + 8 * h + j, 8192),
+                       make_uint2(pack_bf16x2(q[j].x, q[j].y), pack_bf16x2(q[j].z, q[j].w)));
+        if (h == 1) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_XFULL + xs]);
+        }
+        return true;
+      };
+      if (nunits > 0) load32(0, qa);
+      for (uint32_t u = 0; u < nunits && ok; u += 2) {
+        load32(u + 1, qb);
+        if (!(ok = store32(u, qa))) break;
+        if (u + 2 < nunits) load32(u + 2, qa);
+        ok = store32(u + 1, qb);
       }
     }
   } else if (warp == 14) {
@@ -389,7 +431,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
     const unsigned char* os = smem + SM_OS;
     for (int tile = 0; tile < ntiles && ok; ++tile) {
       if (!(ok = bwait(&bars[B_OSREADY], tile & 1, ctx, 402))) break;
-      if (p.occ != nullptr) {
+      if (p.occ != nullptr || p.occ32 != nullptr) {
         const int first_clip = (tile * TILE_M) / S;
 #pragma unroll 1
         for (int grp = 0; grp < 4; ++grp) {
@@ -397,11 +439,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens_kernel(const K1Para
           const int t = tile * TILE_M + tok;
           if (t < ntok) {
             const int clipl = t / S, s = t - clipl * S, slot = clipl - first_clip;
-            __nv_bfloat16* orow = p.occ + ((size_t)(c_begin + clipl) * p.P) * S + s;
+            const size_t o0 = ((size_t)(c_begin + clipl) * p.P) * S + s;
             const unsigned char* src = os + off_mnmajor_nosw(slot * PP, tok, NPOOL);
+            if (!p.f32_in) {
+              __nv_bfloat16* orow = p.occ + o0;
 #pragma unroll 8
-            for (int pp = 0; pp < p.P; ++pp)
-              orow[(size_t)pp * S] = *reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2);
+              for (int pp = 0; pp < p.P; ++pp)
+                orow[(size_t)pp * S] = *reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2);
+            } else {
+              float* orow = p.occ32 + o0;
+#pragma unroll 8
+              for (int pp = 0; pp < p.P; ++pp)
+                orow[(size_t)pp * S] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2));
+            }
           }
         }
       }
@@ -895,7 +945,9 @@ static long long* g_trace = nullptr;
 void sm100_set_trace(void* dev_buf) { g_trace = reinterpret_cast<long long*>(dev_buf); }
 
 bool sm100_supported(const pasn_dims& d) {
-  if (d.dtype != PASN_BF16 || d.layout != PASN_LAYOUT_NCS) return false;
+  // fp32 feature maps take the fused path only on explicit request (bf16 compute: inputs are rounded on the fly)
+  if (d.layout != PASN_LAYOUT_NCS) return false;
+  if (d.dtype != PASN_BF16 && !(d.dtype == PASN_F32 && d.path == PASN_PATH_TCGEN05)) return false;
   if (d.D != DD) return false;
   if (d.C % 64 != 0 || d.C < 64 || d.C > 1024) return false;
   if (d.P < 1 || d.P > PP_MAX) return false;
@@ -957,9 +1009,12 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
 
   const int num_sms = 148;
   K1Params k1{};
+  k1.f32_in = d.dtype == PASN_F32;
   k1.feat = reinterpret_cast<const __nv_bfloat16*>(feat);
+  k1.feat32 = reinterpret_cast<const float*>(feat);
   k1.packed = reinterpret_cast<const uint8_t*>(packed);
-  k1.occ = reinterpret_cast<__nv_bfloat16*>(occ);
+  k1.occ = k1.f32_in ? nullptr : reinterpret_cast<__nv_bfloat16*>(occ);
+  k1.occ32 = k1.f32_in ? reinterpret_cast<float*>(occ) : nullptr;
   k1.feimg = feimg; k1.osum = osum;
   k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.nkc = d.C / 64;
   k1.clips_per_cta = ceil_div(d.N, num_sms);

@@ -573,6 +573,7 @@ static int launch_pair(const K1Params& k1p, cudaStream_t st) {
 }
 
 int launch_k1_pair(const K1Params& k1p, int ppad, cudaStream_t st) {
+  if (k1p.f32_in) return PASN_ERR_UNSUPPORTED;   // fp32 feature maps: single-CTA kernel only
   if (ppad <= 16) return launch_pair<16>(k1p, st);
   if (ppad <= 32) return launch_pair<32>(k1p, st);
   if (ppad <= 40) return launch_pair<40>(k1p, st);

@@ -32,7 +32,10 @@ __host__ __device__ inline PackedLayout packed_layout(int C) {
 }
 
 struct K1Params {
-  const __nv_bfloat16* feat;   // [N][C][S]
+  const __nv_bfloat16* feat;   // [N][C][S] (bf16 input)
+  const float* feat32;         // same buffer seen as fp32 when f32_in (bf16-compute mode for fp32 feature maps)
+  float* occ32;                // occurrence map as fp32 when f32_in
+  int f32_in;
   const uint8_t* packed;
   __nv_bfloat16* occ;          // [N][P][S] or null
   uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile

@@ -70,6 +70,11 @@ __device__ __forceinline__ uint2 ldg_nc_na_v2(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
+__device__ __forceinline__ float4 ldg_nc_na_v4f(const void* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint2 v) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
 }

@@ -210,3 +210,30 @@ def test_cfg2_image_bf16_generic_matches_oracle():
     assert_close(out["similarity"], (1 - rd).numpy(), BF16_RTOL, "similarity")
     assert_close(out["logits"], rl.numpy(), BF16_RTOL, "logits")
     assert_close(out["features_extracted"], rf.numpy(), BF16_RTOL, "features (fp32 math on bf16 inputs)")
+
+
+def test_tcgen05_bf16_compute_on_fp32_features():
+    """Opt-in fused path for fp32 feature maps (the reference's native dtype): inputs are rounded to bf16 on the fly."""
+    dims = synth.CONFIGS["cfg3_video_b1024"]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
+    # (a) bf16-representable fp32 inputs must reproduce the bf16-input run exactly (same kernel arithmetic)
+    x = synth.make_features(dims, 9, seed=3, bf16_round=True)
+    xg = torch.from_numpy(x).cuda()
+    o32 = _run_all(m, xg)
+    o16 = _run_all(m, xg.bfloat16())
+    assert o32["occurrence_map"].dtype == torch.float32
+    assert torch.equal(o32["similarity"], o16["similarity"]) and torch.equal(o32["logits"], o16["logits"])
+    assert torch.equal(o32["features_extracted"], o16["features_extracted"])
+    assert torch.equal(o32["occurrence_map"], o16["occurrence_map"].float())
+    # (b) arbitrary fp32 inputs: within the bf16 budget of the fp32 reference on the unrounded inputs
+    x2 = synth.make_features(dims, 4, seed=5, bf16_round=False)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x2), ho.to_torch_sd(sd))
+    o = _run_all(m, torch.from_numpy(x2).cuda())
+    assert_close(o["similarity"], (1 - rd).numpy(), BF16_RTOL, "similarity")
+    assert_close(o["logits"], rl.numpy(), BF16_RTOL, "logits")
+    # AUTO keeps fp32 inputs on the exact fp32 path
+    m.kernel_path = _lib.PASN_PATH_AUTO
+    oa = _run_all(m, torch.from_numpy(x2).cuda())
+    assert_close(oa["similarity"], (1 - rd).numpy(), FP32_RTOL, "similarity (fp32 path)")
