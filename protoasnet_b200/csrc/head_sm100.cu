@@ -1027,9 +1027,13 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   // The CTA-pair (cta_group::2) variant is correct but measured slower (237 us vs 170 us at cfg 3, N = 1024: its
   // weight relay and cross-CTA hand-offs cost more than the halved weight ingest saves) -- opt-in for experiments.
   static const bool use_pair = [] { const char* e = getenv("PASN_K1_PAIR"); return e && atoi(e) != 0; }();
+  // PASN_K1_PHASES: 2 (default) two-phase kernel, 1 same kernel in serial order, 0 first-generation kernel
+  static const int phases = [] { const char* e = getenv("PASN_K1_PHASES"); return e ? atoi(e) : 2; }();
+  k1.phases = phases;
   main_kernel_begin(st);
   int rc;
   if (use_pair) rc = launch_k1_pair(k1, ppad, st);
+  else if (phases != 0) rc = launch_k1_two_phase(k1, ppad, grid1, st);
   else if (ppad <= 16) rc = launch_k1<16>(k1, grid1, st);
   else if (ppad <= 32) rc = launch_k1<32>(k1, grid1, st);
   else if (ppad <= 40) rc = launch_k1<40>(k1, grid1, st);

@@ -43,6 +43,7 @@ struct K1Params {
   int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / PP
   int* err;
   long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
+  int phases;                  // two-phase kernel: 2 = G / A phases overlapped with the previous chain, 1 = serial order
   int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X
 };
 
@@ -92,6 +93,8 @@ __device__ __forceinline__ void bias_relu_pack(const uint32_t (&r)[32], const fl
 
 }  // namespace k1
 
+// two-phase token kernel (head_sm100_k1.cu)
+int launch_k1_two_phase(const k1::K1Params& k1p, int ppad, int grid, cudaStream_t st);
 // pair variant (head_sm100_pair.cu)
 int launch_k1_pair(const k1::K1Params& k1p, int ppad, cudaStream_t st);
 

@@ -12,7 +12,8 @@
 using namespace pasn::sm100;
 
 struct ProbeCfg {
-  int mode;      // 1: A Kmaj-SW128 x B Kmaj-SW128; 2: A MNmaj-SW128; 3: A in TMEM; 4: A,B MNmaj no-swizzle
+  int mode;      // 1: A Kmaj-SW128 x B Kmaj-SW128; 2: A MNmaj-SW128; 3: A in TMEM; 4: A,B MNmaj no-swizzle;
+                 // 5: A Kmaj-SW128 x B MNmaj-SW128 (weights as A, X tile as B)
   int M, N, K;
   int swap;      // try the alternative convention (LBO<->SBO, or bf16 half order for mode 3)
   int b_row0;    // mode 3: B operand starts at this row of a taller image
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     for (int i = tid; i < M * K; i += 128) {
       int m = i / K, k = i % K;
       uint32_t off;
-      if (c.mode == 1) off = off_kmajor_sw128(m, k);
+      if (c.mode == 1 || c.mode == 5) off = off_kmajor_sw128(m, k);
       else if (c.mode == 2) off = off_mnmajor_sw128(m, k, 8192);
       else off = off_mnmajor_nosw(m, k, M);
       *(__nv_bfloat16*)(As + off) = __float2bfloat16_rn(A[i]);
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     int n = i / K, k = i % K;
     uint32_t off;
     if (c.mode == 4) off = off_mnmajor_nosw(n, k, N);
+    else if (c.mode == 5) off = off_mnmajor_sw128(n, k, 8192);
     else off = off_kmajor_sw128(n + c.b_row0, k);
     *(__nv_bfloat16*)(Bs + off) = __float2bfloat16_rn(B[i]);
   }
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     if (c.mode == 1) idesc = make_idesc_bf16(M, N, 0, 0);
     else if (c.mode == 2) idesc = make_idesc_bf16(M, N, 1, 0);
     else if (c.mode == 3) idesc = make_idesc_bf16(M, N, 0, 0);
+    else if (c.mode == 5) idesc = make_idesc_bf16(M, N, 0, 1);
     else idesc = make_idesc_bf16(M, N, 1, 1);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t bdesc;
@@ -88,6 +91,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
         uint32_t lbo = (N / 8) * 128, sbo = 128;
         bdesc = c.swap ? make_smem_desc(smem_u32(Bs) + ks * 2 * lbo, sbo, lbo, SWZ_NONE)
                        : make_smem_desc(smem_u32(Bs) + ks * 2 * lbo, lbo, sbo, SWZ_NONE);
+      } else if (c.mode == 5) {
+        bdesc = make_smem_desc(smem_u32(Bs) + ks * 2048, 8192, 1024, SWZ_128B);
       } else {
         bdesc = make_smem_desc(smem_u32(Bs) + c.b_row0 * 128 + ks * 32, 16, 1024, SWZ_128B);
       }
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
         mma_ts(tbase, tbase + 256 + ks * 8, bdesc, idesc, ks > 0);
       } else {
         uint64_t adesc;
-        if (c.mode == 1) adesc = make_smem_desc(smem_u32(As) + ks * 32, 16, 1024, SWZ_128B);
+        if (c.mode == 1 || c.mode == 5) adesc = make_smem_desc(smem_u32(As) + ks * 32, 16, 1024, SWZ_128B);
         else if (c.mode == 2)
           adesc = c.swap ? make_smem_desc(smem_u32(As) + ks * 2048, 1024, 8192, SWZ_128B)
                          : make_smem_desc(smem_u32(As) + ks * 2048, 8192, 1024, SWZ_128B);
@@ -173,6 +178,7 @@ int main() {
   pass += run("T3c TS A in TMEM, N=128, B row0=0", {3, 128, 128, 64, 0, 0});
   pass += run("T4 SS  A,B MNmaj no-swizzle (LBO=k-grp, SBO=mn-grp)", {4, 128, 80, 128, 0, 0});
   pass += run("T4s SS A,B MNmaj no-swizzle (swapped)", {4, 128, 80, 128, 1, 0});
+  pass += run("T5 SS  A Kmaj-SW128, B MNmaj-SW128 N=128", {5, 128, 128, 64, 0, 0});
   printf("passed %d\n", pass);
   return 0;
 }
