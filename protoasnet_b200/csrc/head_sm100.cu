@@ -1027,8 +1027,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   // The CTA-pair (cta_group::2) variant is correct but measured slower (237 us vs 170 us at cfg 3, N = 1024: its
   // weight relay and cross-CTA hand-offs cost more than the halved weight ingest saves) -- opt-in for experiments.
   static const bool use_pair = [] { const char* e = getenv("PASN_K1_PAIR"); return e && atoi(e) != 0; }();
-  // PASN_K1_PHASES: 2 (default) two-phase kernel, 1 same kernel in serial order, 0 first-generation kernel
-  static const int phases = [] { const char* e = getenv("PASN_K1_PHASES"); return e ? atoi(e) : 2; }();
+  // PASN_K1_PHASES: 2 two-phase kernel, 1 same kernel in serial order, 0 (default) first-generation kernel
+  static const int phases = [] { const char* e = getenv("PASN_K1_PHASES"); return e ? atoi(e) : 0; }();
   k1.phases = phases;
   main_kernel_begin(st);
   int rc;

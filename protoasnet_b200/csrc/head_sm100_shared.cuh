@@ -52,19 +52,23 @@ struct Ctx {
   volatile int* abort_s;
 };
 
-// bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug
-__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
+// bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug.  The spin is
+// out of line so that the fast path at every call site is a single try_wait.
+static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, int* err, volatile int* abort_s, int code) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (*c.abort_s) return false;
+    if (*abort_s) return false;
     if (clock64() - t0 > 4000000000ll) {
-      *c.abort_s = 1;
-      atomicCAS(c.err, 0, code);
+      *abort_s = 1;
+      atomicCAS(err, 0, code);
       return false;
     }
   }
   return true;
+}
+__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return bwait_slow(bar, parity, c.err, c.abort_s, code);
 }
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {

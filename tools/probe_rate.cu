@@ -113,6 +113,43 @@ __global__ void __launch_bounds__(256) rate_kernel(int mode, int random, long lo
       }
       if (blockIdx.x == 0 && tid == 128) out[14] = n;
     }
+  } else if (mode >= 23 && mode <= 34) {
+    // issue blocks (23-28: 8 x N128 SS, 29-34: 4 x N256 SS) + one commit, separated by a dependent ALU chain of
+    // 0 / 16 / 32 / 64 / 128 / 256 multiply-adds in the issuing thread: how much preparation fits between two blocks?
+    __shared__ uint64_t sink[8];
+    if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(&sink[i], 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      const bool n128 = mode <= 28;
+      const int gsel = n128 ? mode - 23 : mode - 29;
+      const int gap = gsel == 0 ? 0 : (8 << gsel);
+      const uint32_t ida = make_idesc_bf16(128, 128, 0, 1), idg = make_idesc_bf16(128, 256, 1, 0);
+      uint32_t junk = (uint32_t)clock64();
+      const long long t0 = clock64();
+      for (int c = 0; c < ITER / 8; ++c) {
+        const int slot = c & 3, ws = c & 1;
+        if (n128) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k4 = j & 3, h = j >> 2;
+            mma_ss_x(tbase + 256u + 128u * h, desc_lo(b0 + ws * 32768 + h * 16384 + k4 * 32, 16), desc_hi(1024, SWZ_128B),
+                     desc_lo(a0 + slot * 16384 + k4 * 2048, 8192), desc_hi(1024, SWZ_128B), ida, c ? 1u : (uint32_t)(k4 != 0));
+          }
+        } else {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            mma_ss_x(tbase, desc_lo(a0 + slot * 16384 + k4 * 2048, 8192), desc_hi(1024, SWZ_128B),
+                     desc_lo(b0 + ws * 32768 + k4 * 32, 16), desc_hi(1024, SWZ_128B), idg, c ? 1u : (uint32_t)(k4 != 0));
+        }
+        mma_commit(&sink[c & 7]);
+        for (int g = 0; g < gap; ++g) junk = junk * 1664525u + 1013904223u;
+      }
+      const long long t1 = clock64();
+      mma_commit(&bar[0]);
+      mbar_wait(&bar[0], 0, err, 1);
+      const long long t2 = clock64();
+      if (blockIdx.x == 0) { out[2] = t1 - t0; out[3] = (t2 - t0) * (n128 ? 1 : 2); out[15] = junk; }
+    }
   } else if (mode >= 15 && mode <= 22) {
     // commit interval sweep: 15-18 shape 0 (N256) with a commit every 2 / 4 / 8 / 16 MMAs; 19-22 shape 1 (N128) every 4 / 8 / 16 / 32
     __shared__ uint64_t sink[8];
@@ -241,12 +278,14 @@ int main() {
                          "SS N128 + bulk + cp.async streams", "SS N128 + 7 spinning warps", "SS N256 + 7 spinning warps", "SS N128 chunks: 1 commit", "SS N128 chunks: 2 commits",
                          "SS N128 chunks: 2 commits + 2 waits", "SS N128 chunks: 2 commits + 2 waits + fence",
                          "N256 commit every 2", "N256 commit every 4", "N256 commit every 8", "N256 commit every 16",
-                         "N128 commit every 4", "N128 commit every 8", "N128 commit every 16", "N128 commit every 32"};
+                         "N128 commit every 4", "N128 commit every 8", "N128 commit every 16", "N128 commit every 32",
+                         "8xN128 block, gap 0", "8xN128 block, gap 16", "8xN128 block, gap 32", "8xN128 block, gap 64", "8xN128 block, gap 128", "8xN128 block, gap 256",
+                         "4xN256 block, gap 0 (x2)", "4xN256 block, gap 16 (x2)", "4xN256 block, gap 32 (x2)", "4xN256 block, gap 64 (x2)", "4xN256 block, gap 128 (x2)", "4xN256 block, gap 256 (x2)"};
   unsigned char *wsrc, *xsrc;
   cudaMalloc(&wsrc, 1 << 20); cudaMemset(wsrc, 0, 1 << 20);
   cudaMalloc(&xsrc, (size_t)148 << 20); cudaMemset(xsrc, 0, (size_t)148 << 20);
   for (int random = 1; random < 2; ++random)
-  for (int mode = 15; mode < 23; ++mode) {
+  for (int mode = 23; mode < 35; ++mode) {
     cudaMemset(d_out, 0, 16 * 8); cudaMemset(d_err, 0, 4);
     for (int rep = 0; rep < 3; ++rep) rate_kernel<<<148, 256, 164 * 1024>>>(mode, random, d_out, d_err, wsrc, xsrc);
     cudaError_t e = cudaDeviceSynchronize();
