@@ -194,20 +194,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         wr = mbar_test_wait(&bars[B_WFULL + ws], wph);
         return r;
       };
-      auto chunk_g = [&](int kc, uint32_t sx, bool free_x) -> bool {   // 4 MMAs: one 64-channel chunk into acc_G
-        uint32_t sw;
-        if (!take_w(sw)) return false;
+      auto issue_g = [&](int kc, uint32_t sx, uint32_t sw, bool free_x) {   // 4 MMAs: one 64-channel chunk into acc_G
         const uint32_t alo = x_lo0 + sx * (XSLOT_BYTES >> 4), blo = w_lo0 + sw * (WSLOT_BYTES >> 4);
         mma_ss_x(tb, alo, HI_SW128, blo, HI_SW128, idesc_g, kc ? 1u : 0u);
 #pragma unroll
         for (int k4 = 1; k4 < 4; ++k4) mma_ss_x(tb, alo + k4 * 128, HI_SW128, blo + k4 * 2, HI_SW128, idesc_g, 1u);
         mma_commit_a(baddr(B_WEMPTY) + 8u * sw);
         if (free_x) mma_commit_a(baddr(B_XEMPTY) + 8u * sx);
-        return true;
       };
-      auto chunk_a = [&](int kc, uint32_t sx) -> bool {   // 8 MMAs: one chunk into both channel halves of acc_A^T
-        uint32_t sw;
-        if (!take_w(sw)) return false;
+      auto issue_a = [&](int kc, uint32_t sx, uint32_t sw) {   // 8 MMAs: one chunk into both channel halves of acc_A^T
         const uint32_t blo = x_lo0 + sx * (XSLOT_BYTES >> 4), alo = w_lo0 + sw * (WSLOT_BYTES >> 4);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -218,6 +213,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         }
         mma_commit_a(baddr(B_WEMPTY) + 8u * sw);
         mma_commit_a(baddr(B_XEMPTY) + 8u * sx);
+      };
+      auto chunk_g = [&](int kc, uint32_t sx, bool free_x) -> bool {
+        uint32_t sw;
+        if (!take_w(sw)) return false;
+        issue_g(kc, sx, sw, free_x);
+        return true;
+      };
+      auto chunk_a = [&](int kc, uint32_t sx) -> bool {
+        uint32_t sw;
+        if (!take_w(sw)) return false;
+        issue_a(kc, sx, sw);
         return true;
       };
       // Weight stages that belong to the tail issuer (W4a, W4b, W5) sit at fixed positions of the stream.  This thread
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         } else {
           if (!(ok = bwait(&bars[B_ABFREE], tp ^ 1, ctx, 111))) break;
           tc_fence_after();
+          stamp(tile, 3);
           for (int kc = 0; kc < nkc && ok; ++kc) {
             long long tc0 = 0;
             if constexpr (TRACE) tc0 = clock64();
@@ -361,14 +368,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         // ---- pooling FEpartial^T = H1^T O, one channel half after the other (they share the FEpartial^T columns)
 #pragma unroll
         for (int step = 0; step < 2; ++step) {
+          // two-phase: both halves go through columns [320, 320+NPOOL) (the G-branch columns already belong to the next
+          // tile), so half 1 waits for half 0 to be drained.  Serial order: half 1 lands in the idle G-branch columns
+          // [0, NPOOL) and is issued back to back.
           if (step == 0) ok = bwait(&bars[B_H1TREADY], tp, ctx, 108) && bwait(&bars[B_OSREADY], tp, ctx, 109);
-          else ok = bwait(&bars[B_FEFREE0], tp, ctx, 110);
+          else if (two_phase) ok = bwait(&bars[B_FEFREE0], tp, ctx, 110);
           if (!ok) break;
           tc_fence_after();
           const uint32_t a0 = step ? COL_H1T1 : COL_H1T0;
+          const uint32_t d0 = (step && !two_phase) ? 0u : COL_FE;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            mma_ts_x(tb + COL_FE, tb + a0 + 8u * ks, os_lo0 + ks * (2 * lbo_os / 16), HI_OS, idesc_pool, ks ? 1u : 0u);
+            mma_ts_x(tb + d0, tb + a0 + 8u * ks, os_lo0 + ks * (2 * lbo_os / 16), HI_OS, idesc_pool, ks ? 1u : 0u);
           if (step == 0) mma_commit_a(baddr(B_FEDONE0));
           else { mma_commit_a(baddr(B_FEDONE1)); mma_commit_a(baddr(B_OSEMPTY)); }
           if constexpr (TRACE) K1_TRACE(0, tile, 7 + step);
@@ -725,7 +736,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const int last_clip = last_tok / S;
         const bool boundary = last_clip > first_clip;
         const bool ends = ((last_tok + 1) % S) == 0;
-        const uint32_t fe = tl + COL_FE;
+        const uint32_t fe = tl + ((hh && !two_phase) ? 0u : COL_FE);   // serial order: half 1 sits in the G-branch columns
         uint32_t nb[PP];  // slot-1 partial = start of the next clip (only meaningful when `boundary`)
         {
           uint32_t a[PP];
