@@ -153,9 +153,13 @@ int pasn_debug_time_main_kernel(int enable);
 float pasn_debug_last_main_kernel_ms(void);
 /* synchronises `stream` and returns the bounded-wait error code the fused tcgen05 kernels left in `workspace`
  * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid) */
-/* device buffer of 2*16*16 int64 that CTA 0 of the fused kernel fills with clock64() stamps per tile phase (NULL = off) */
-int pasn_debug_set_trace(void* device_buffer);
 int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream);
+/* device buffer of 3*16*16 int64 that CTA 0 of the fused kernel fills with clock64() stamps per tile phase (NULL = off) */
+int pasn_debug_set_trace(void* device_buffer);
+/* which implementation of the fused token kernel the next calls use (all produce the same results; kept for A/B timing
+ * and regression tests): 1 = current kernel, serial tile order (default); 2 = same kernel, two-phase order;
+ * 0 = first-generation kernel; 3 = CTA-pair (cta_group::2) variant; -1 = back to the default / PASN_K1_PHASES */
+int pasn_debug_set_k1_variant(int variant);
 
 #ifdef __cplusplus
 }

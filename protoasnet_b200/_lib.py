@@ -23,7 +23,7 @@ SYMBOLS = [
     "pasn_packed_weights_bytes", "pasn_pack_weights", "pasn_head_forward", "pasn_occurrence_only",
     "pasn_push_init", "pasn_push_decode", "pasn_push_select", "pasn_push_collect", "pasn_push_write_prototypes",
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
-    "pasn_debug_sm100_error", "pasn_debug_set_trace",
+    "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant",
 ]
 
 
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     lib.pasn_debug_last_main_kernel_ms.restype = C.c_float
     lib.pasn_debug_set_trace.restype = C.c_int
     lib.pasn_debug_set_trace.argtypes = [vp]
+    lib.pasn_debug_set_k1_variant.restype = C.c_int
+    lib.pasn_debug_set_k1_variant.argtypes = [C.c_int]
     lib.pasn_debug_sm100_error.restype = C.c_int
     lib.pasn_debug_sm100_error.argtypes = [vp, C.POINTER(PasnDims), vp]
     if lib.pasn_abi_version() != 1:

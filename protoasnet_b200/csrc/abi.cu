@@ -53,6 +53,7 @@ extern "C" int pasn_debug_sm100_error(const void* workspace, const pasn_dims* di
 }
 
 extern "C" int pasn_debug_set_trace(void* device_buffer) { sm100_set_trace(device_buffer); return PASN_OK; }
+extern "C" int pasn_debug_set_k1_variant(int variant) { sm100_set_k1_variant(variant); return PASN_OK; }
 
 extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
 

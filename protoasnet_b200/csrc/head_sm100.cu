@@ -943,6 +943,8 @@ __global__ void pack_weights_kernel(pasn_weights w, int C, int P, uint8_t* out) 
 // =================================================================================================
 static long long* g_trace = nullptr;
 void sm100_set_trace(void* dev_buf) { g_trace = reinterpret_cast<long long*>(dev_buf); }
+static int g_k1_variant = -1;   // -1: PASN_K1_PHASES / PASN_K1_PAIR from the environment, else the default
+void sm100_set_k1_variant(int variant) { g_k1_variant = variant; }
 
 bool sm100_supported(const pasn_dims& d) {
   // fp32 feature maps take the fused path only on explicit request (bf16 compute: inputs are rounded on the fly)
@@ -1024,11 +1026,20 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
   const int grid1 = ceil_div(d.N, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
-  // The CTA-pair (cta_group::2) variant is correct but measured slower (237 us vs 170 us at cfg 3, N = 1024: its
-  // weight relay and cross-CTA hand-offs cost more than the halved weight ingest saves) -- opt-in for experiments.
-  static const bool use_pair = [] { const char* e = getenv("PASN_K1_PAIR"); return e && atoi(e) != 0; }();
-  // PASN_K1_PHASES: 2 two-phase kernel, 1 same kernel in serial order, 0 (default) first-generation kernel
-  static const int phases = [] { const char* e = getenv("PASN_K1_PHASES"); return e ? atoi(e) : 0; }();
+  // Token-kernel variants (same results; see profiles/README.md for the measurements):
+  //   1  head_sm100_k1.cu, serial tile order -- the default
+  //   2  head_sm100_k1.cu, two-phase order (G / A phases overlapped with the previous tile's chain)
+  //   0  first-generation kernel in this file
+  //   3  CTA-pair (cta_group::2) variant, head_sm100_pair.cu
+  static const int env_variant = [] {
+    const char* e = getenv("PASN_K1_PAIR");
+    if (e && atoi(e) != 0) return 3;
+    e = getenv("PASN_K1_PHASES");
+    return e ? atoi(e) : 1;
+  }();
+  const int variant = g_k1_variant >= 0 ? g_k1_variant : env_variant;
+  const bool use_pair = variant == 3 && !k1.f32_in;
+  const int phases = variant == 3 ? 1 : variant;
   k1.phases = phases;
   main_kernel_begin(st);
   int rc;

@@ -28,7 +28,10 @@ using namespace k1;
 
 namespace {
 
-constexpr int XSLOTS = 4, WSLOTS = 3, XDEPTH = 3;   // XDEPTH chunks of cp.async in flight per producer warp
+#ifndef PASN_XSLOTS
+#define PASN_XSLOTS 4
+#endif
+constexpr int XSLOTS = PASN_XSLOTS, WSLOTS = 3, XDEPTH = XSLOTS - 1;   // XDEPTH chunks of cp.async in flight per producer warp
 constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768;
 constexpr int K1_WARPS = 16, K1_THREADS = K1_WARPS * 32;
 constexpr int W_MMA = 0, W_WPROD = 1, W_TAIL = 2, W_OCC = 3, W_X0 = 4, W_EPI0 = 8;
@@ -39,15 +42,15 @@ constexpr uint32_t SM_OS = SM_W + WSLOTS * WSLOT_BYTES;           // 163840
 constexpr uint32_t OS_BYTES_MAX = TILE_M * 2 * PP_MAX * 2;        // 24576
 constexpr uint32_t SM_BIAS = SM_OS + OS_BYTES_MAX;                // 188416  b3[256] b1[256] b4[128] fp32
 constexpr uint32_t SM_BAR = SM_BIAS + (DD + DD + DH) * 4;         // 190976
-constexpr uint32_t SM_MISC = SM_BAR + 32 * 8;                     // 191232
+constexpr uint32_t SM_MISC = SM_BAR + 36 * 8;                     // 191232
 constexpr uint32_t K1_SMEM = SM_MISC + 64;                        // 191296
-static_assert(K1_SMEM <= 195 * 1024, "keep the 196 KB carve-out (60 KB of L1 for the cp.async gather)");
+static_assert(PASN_XSLOTS != 4 || K1_SMEM <= 195 * 1024, "keep the 196 KB carve-out (60 KB of L1 for the cp.async gather)");
 
 enum {
-  B_XFULL = 0, B_XEMPTY = 4, B_WFULL = 8, B_WEMPTY = 11, B_GDONE = 14, B_ADONE, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
+  B_XFULL = 0, B_XEMPTY = XSLOTS, B_WFULL = 2 * XSLOTS, B_WEMPTY = 2 * XSLOTS + 3, B_GDONE = 2 * XSLOTS + 6, B_ADONE, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
   B_OSREADY, B_OSEMPTY, B_H1TREADY, B_FEDONE0, B_FEFREE0, B_FEDONE1, B_GBFREE, B_ABFREE, B_W4RDY, B_W5RDY, B_COUNT
 };
-static_assert(B_COUNT <= 32, "barrier table");
+static_assert(B_COUNT <= 36, "barrier table");
 
 // TMEM columns (512 x 128 lanes)
 //   GB [  0,256)  acc_G fp32 (lane = voxel) -> G1 bf16 at [0,64) + [192,256) -> acc_G2 fp32 [64,192) -> G2 bf16 at
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           if constexpr (TRACE) xwait += clock64() - t0;
         }
         ++xcount;
-        xs = (xs + 1) & (XSLOTS - 1);
+        xs = xs + 1 == XSLOTS ? 0 : xs + 1;
         xph ^= (xs == 0) ? 1u : 0u;
         xr = xcount < njobs && mbar_test_wait(&bars[B_XFULL + xs], xph);
         return r;

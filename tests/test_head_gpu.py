@@ -237,3 +237,34 @@ def test_tcgen05_bf16_compute_on_fp32_features():
     m.kernel_path = _lib.PASN_PATH_AUTO
     oa = _run_all(m, torch.from_numpy(x2).cuda())
     assert_close(oa["similarity"], (1 - rd).numpy(), FP32_RTOL, "similarity (fp32 path)")
+
+
+VARIANT_SHAPES = [(512, 40, 4, (4, 7, 7), 37), (256, 24, 4, (8, 14, 14), 2), (128, 12, 3, (1, 10, 14), 5)]
+
+
+@pytest.mark.parametrize("shape", VARIANT_SHAPES, ids=[str(s) for s in VARIANT_SHAPES])
+def test_token_kernel_variants_agree(shape):
+    """The kept implementations of the fused token kernel (current serial / two-phase order, first generation, CTA
+    pair) are interchangeable: same TMEM-accumulated math, so results agree to accumulation-order noise, and each stays
+    inside the bf16 budget against the generic CUDA path."""
+    C, P, K, spatial, n = shape
+    dims = synth.HeadDims(C, 256, P, K, spatial)
+    sd = synth.make_head_params(dims, seed=77, bias_scale=0.05, last_layer_noise=0.1, bf16_round=True)
+    xg = torch.from_numpy(synth.make_features(dims, n, seed=29, bf16_round=True)).cuda().bfloat16()
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
+    ref = _run_all(build_model(dims, sd, path=_lib.PASN_PATH_GENERIC), xg)
+    lib = _lib.load()
+    outs = {}
+    try:
+        for variant in (1, 2, 0, 3):
+            lib.pasn_debug_set_k1_variant(variant)
+            outs[variant] = _run_all(m, xg)
+            torch.cuda.synchronize()
+    finally:
+        lib.pasn_debug_set_k1_variant(-1)
+    for variant, out in outs.items():
+        assert_close(out["similarity"], ref["similarity"].cpu().numpy(), BF16_RTOL, f"similarity, variant {variant}")
+        assert_close(out["logits"], ref["logits"].cpu().numpy(), BF16_RTOL, f"logits, variant {variant}")
+        assert_close(out["similarity"], outs[1]["similarity"].cpu().numpy(), 1e-4, f"variant {variant} vs default")
+        assert_close(out["features_extracted"], outs[1]["features_extracted"].cpu().numpy(), 1e-4, f"features, variant {variant}")
+        assert torch.equal(out["occurrence_map"], outs[1]["occurrence_map"]), f"occurrence map, variant {variant}"
