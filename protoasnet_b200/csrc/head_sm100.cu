@@ -948,7 +948,8 @@ void sm100_set_k1_variant(int variant) { g_k1_variant = variant; }
 
 bool sm100_supported(const pasn_dims& d) {
   // fp32 feature maps take the fused path only on explicit request (bf16 compute: inputs are rounded on the fly)
-  if (d.layout != PASN_LAYOUT_NCS) return false;
+  // channels_last ([N,S,C]) feature maps: bf16 only
+  if (d.layout != PASN_LAYOUT_NCS && !(d.layout == PASN_LAYOUT_NSC && d.dtype == PASN_BF16)) return false;
   if (d.dtype != PASN_BF16 && !(d.dtype == PASN_F32 && d.path == PASN_PATH_TCGEN05)) return false;
   if (d.D != DD) return false;
   if (d.C % 64 != 0 || d.C < 64 || d.C > 1024) return false;
@@ -1012,6 +1013,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   const int num_sms = 148;
   K1Params k1{};
   k1.f32_in = d.dtype == PASN_F32;
+  k1.nsc = d.layout == PASN_LAYOUT_NSC;
   k1.feat = reinterpret_cast<const __nv_bfloat16*>(feat);
   k1.feat32 = reinterpret_cast<const float*>(feat);
   k1.packed = reinterpret_cast<const uint8_t*>(packed);
@@ -1037,7 +1039,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
     e = getenv("PASN_K1_PHASES");
     return e ? atoi(e) : 1;
   }();
-  const int variant = g_k1_variant >= 0 ? g_k1_variant : env_variant;
+  int variant = g_k1_variant >= 0 ? g_k1_variant : env_variant;
+  if (k1.nsc && (variant == 0 || variant == 3)) variant = 1;   // only the current kernel gathers channels_last input
   const bool use_pair = variant == 3 && !k1.f32_in;
   const int phases = variant == 3 ? 1 : variant;
   k1.phases = phases;

@@ -148,8 +148,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       auto stamp = [&](int tile, int slot) {
         if constexpr (TRACE) K1_TRACE(0, tile, slot);
       };
-      const uint32_t idesc_g = make_idesc_bf16(128, 256, 1, 0);    // A = X tile (MN-major), B = W3 chunk (K-major)
-      const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, 1);    // A = W1 half chunk (K-major), B = X tile (MN-major)
+      // X tile: MN-major (voxels contiguous) for NCDHW input, K-major (channels contiguous) for channels_last input
+      const uint32_t x_mn = p.nsc ? 0u : 1u;
+      const uint32_t idesc_g = make_idesc_bf16(128, 256, x_mn, 0);    // A = X tile, B = W3 chunk (K-major)
+      const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, x_mn);    // A = W1 half chunk (K-major), B = X tile
+      const uint32_t xk = p.nsc ? 2u : 128u;                          // descriptor advance per K step of 16 channels
       const uint32_t idesc_g2 = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_pool = make_idesc_bf16(128, NPOOL, 0, 1);  // A = H1^T in TMEM, B = Os (MN-major, no swizzle)
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       constexpr uint32_t HI_SW128 = desc_hi(1024, SWZ_128B);   // X tile (MN-major) and weight images (K-major): SBO 1024
       constexpr uint32_t HI_OS = desc_hi(128, SWZ_NONE);       // Os: MN-major, no swizzle, SBO 128
       const uint32_t tb = tbase;
-      const uint32_t x_lo0 = desc_lo(x_base, 8192), w_lo0 = desc_lo(w_base, 16), os_lo0 = desc_lo(os_base, lbo_os);
+      const uint32_t x_lo0 = desc_lo(x_base, p.nsc ? 16u : 8192u), w_lo0 = desc_lo(w_base, 16), os_lo0 = desc_lo(os_base, lbo_os);
       const uint32_t bar0 = smem_u32(bars);
       auto baddr = [&](int b) -> uint32_t { return bar0 + 8u * (uint32_t)b; };
       const uint32_t njobs = (uint32_t)ntiles * (uint32_t)nkc * (two_phase ? 2u : 1u);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const uint32_t alo = x_lo0 + sx * (XSLOT_BYTES >> 4), blo = w_lo0 + sw * (WSLOT_BYTES >> 4);
         mma_ss_x(tb, alo, HI_SW128, blo, HI_SW128, idesc_g, kc ? 1u : 0u);
 #pragma unroll
-        for (int k4 = 1; k4 < 4; ++k4) mma_ss_x(tb, alo + k4 * 128, HI_SW128, blo + k4 * 2, HI_SW128, idesc_g, 1u);
+        for (int k4 = 1; k4 < 4; ++k4) mma_ss_x(tb, alo + k4 * xk, HI_SW128, blo + k4 * 2, HI_SW128, idesc_g, 1u);
         mma_commit_a(baddr(B_WEMPTY) + 8u * sw);
         if (free_x) mma_commit_a(baddr(B_XEMPTY) + 8u * sx);
       };
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           mma_ss_x(tb + COL_AT + 128u * h, alo + h * 1024, HI_SW128, blo, HI_SW128, idesc_a, kc ? 1u : 0u);
 #pragma unroll
           for (int k4 = 1; k4 < 4; ++k4)
-            mma_ss_x(tb + COL_AT + 128u * h, alo + h * 1024 + k4 * 2, HI_SW128, blo + k4 * 128, HI_SW128, idesc_a, 1u);
+            mma_ss_x(tb + COL_AT + 128u * h, alo + h * 1024 + k4 * 2, HI_SW128, blo + k4 * xk, HI_SW128, idesc_a, 1u);
         }
         mma_commit_a(baddr(B_WEMPTY) + 8u * sw);
         mma_commit_a(baddr(B_XEMPTY) + 8u * sx);
@@ -433,7 +436,42 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
     const uint32_t jobs_per_tile = (uint32_t)nkc * (two_phase ? 2u : 1u);
     const uint32_t njobs = (uint32_t)ntiles * jobs_per_tile;
     bool ok = true;
-    if (!p.f32_in) {
+    if (p.nsc) {
+      // channels_last feature map [N][S][C]: a voxel's 64 channels of a chunk are 128 contiguous, 16-byte aligned bytes,
+      // i.e. one row of the K-major SWIZZLE_128B operand image.  16-byte L1-bypassing cp.async: eight lanes per voxel row,
+      // four rows per warp instruction, 32 rows per warp.  Voxels of consecutive clips are contiguous in this layout.
+      uint32_t pub = 0;
+      auto publish = [&]() {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_XFULL + (pub % XSLOTS)]);
+        ++pub;
+      };
+      const int sub = lane & 7, r4 = lane >> 3;
+      for (uint32_t g = 0; g < njobs; ++g) {
+        const uint32_t xs = g % XSLOTS, xph = (g / XSLOTS) & 1;
+        if (!(ok = bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301))) break;
+        const int tile = (int)(g / jobs_per_tile);
+        const int kc = (int)((g - (uint32_t)tile * jobs_per_tile) % (uint32_t)nkc);
+        const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
+        const __nv_bfloat16* src0 = p.feat + ((size_t)c_begin * S + (size_t)tile * TILE_M) * p.C + kc * 64 + sub * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = xw * 32 + j * 4 + r4;
+          const bool valid = tile * TILE_M + row < ntok && !(p.dbg_skip & 2);
+          cp_async_16(dst0 + off_kmajor_sw128(row, sub * 8), src0 + (size_t)(valid ? row : 0) * p.C, valid ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (g >= XDEPTH - 1) {
+          cp_async_wait<XDEPTH - 1>();
+          publish();
+        }
+      }
+      if (ok) {
+        cp_async_wait<0>();
+        while (pub < njobs) publish();
+      }
+    } else if (!p.f32_in) {
       uint32_t pub = 0;
       auto publish = [&]() {
         fence_proxy_async();

@@ -36,6 +36,7 @@ struct K1Params {
   const float* feat32;         // same buffer seen as fp32 when f32_in (bf16-compute mode for fp32 feature maps)
   float* occ32;                // occurrence map as fp32 when f32_in
   int f32_in;
+  int nsc;                     // feature map is [N][S][C] (channels_last): two-phase kernel file only, bf16 only
   const uint8_t* packed;
   __nv_bfloat16* occ;          // [N][P][S] or null
   uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile

@@ -268,3 +268,29 @@ def test_token_kernel_variants_agree(shape):
         assert_close(out["similarity"], outs[1]["similarity"].cpu().numpy(), 1e-4, f"variant {variant} vs default")
         assert_close(out["features_extracted"], outs[1]["features_extracted"].cpu().numpy(), 1e-4, f"features, variant {variant}")
         assert torch.equal(out["occurrence_map"], outs[1]["occurrence_map"]), f"occurrence map, variant {variant}"
+
+
+@pytest.mark.parametrize("shape", [(512, 40, 4, (4, 7, 7), 37), (256, 24, 4, (8, 14, 14), 2), (64, 8, 4, (2, 8, 8), 3),
+                                   (1024, 40, 8, (3, 8, 8), 2)], ids=str)
+def test_tcgen05_channels_last_input(shape):
+    """A channels_last_3d bf16 feature map ([N,S,C] in memory) takes the fused path directly (K-major X tile, 16-byte
+    cp.async gather) and gives the same results as the NCDHW gather: same MMAs in the same order."""
+    C, P, K, spatial, n = shape
+    dims = synth.HeadDims(C, 256, P, K, spatial)
+    sd = synth.make_head_params(dims, seed=5, bias_scale=0.05, last_layer_noise=0.1, bf16_round=True)
+    x = torch.from_numpy(synth.make_features(dims, n, seed=31, bf16_round=True)).cuda().bfloat16()
+    xcl = x.contiguous(memory_format=torch.channels_last_3d)
+    assert not xcl.is_contiguous() and xcl.is_contiguous(memory_format=torch.channels_last_3d)
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
+    lib = _lib.load()
+    ref = _run_all(m, x)
+    try:
+        for variant in (1, 2):
+            lib.pasn_debug_set_k1_variant(variant)
+            out = _run_all(m, xcl)
+            for k in ("logits", "similarity", "features_extracted", "distance"):
+                assert_close(out[k], ref[k].cpu().numpy(), 1e-5, f"{k}, channels_last, variant {variant}")
+            assert out["occurrence_map"].shape == ref["occurrence_map"].shape
+            assert torch.equal(out["occurrence_map"], ref["occurrence_map"])
+    finally:
+        lib.pasn_debug_set_k1_variant(-1)
