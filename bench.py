@@ -247,6 +247,32 @@ def main():
     value = world * BATCH / (ms_step * 1e-3)
     main_ms_avg = float(np.mean(main_ms))
 
+    # side measurement (not the headline): the same batch handed over as a channels_last_3d tensor ([N,S,C] in memory,
+    # what a channels_last bf16 backbone emits) -- the fused path gathers it with 16-byte L1-bypassing cp.async
+    channels_last = None
+    if tc and rank == 0:
+        xcl = x.contiguous(memory_format=torch.channels_last_3d)
+        with torch.no_grad():
+            for _ in range(3):
+                model(xcl)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(args.steps):
+                model(xcl)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            cl_ms = e0.elapsed_time(e1) / args.steps
+            lib.pasn_debug_time_main_kernel(1)
+            cl_main = []
+            for _ in range(args.steps):
+                model(xcl)
+                cl_main.append(float(lib.pasn_debug_last_main_kernel_ms()))
+            lib.pasn_debug_time_main_kernel(0)
+        channels_last = {"value_one_gpu": BATCH / (cl_ms * 1e-3), "unit": "clips/s", "ms_per_step": cl_ms,
+                         "kernel_ms": float(np.mean(cl_main)),
+                         "frac_of_burst": BATCH * flops_clip / (float(np.mean(cl_main)) * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        del xcl
+
     # ---------------- end to end through the public API with host buffers ----------------
     x_host = x.cpu().pin_memory()
     lg_host = torch.empty((BATCH, dims.K), dtype=torch.float32).pin_memory()
@@ -352,6 +378,7 @@ def main():
                          "hbm_gbs": BATCH * bytes_clip / (main_ms_avg * 1e-3) / 1e9,
                          "hbm_frac": BATCH * bytes_clip / (main_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "push": push,
+            "channels_last": channels_last,
         }
         print(json.dumps(line))
     if world > 1:

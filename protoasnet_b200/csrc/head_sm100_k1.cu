@@ -31,7 +31,10 @@ namespace {
 #ifndef PASN_XSLOTS
 #define PASN_XSLOTS 4
 #endif
-constexpr int XSLOTS = PASN_XSLOTS, WSLOTS = 3, XDEPTH = XSLOTS - 1;   // XDEPTH chunks of cp.async in flight per producer warp
+#ifndef PASN_WSLOTS
+#define PASN_WSLOTS 3
+#endif
+constexpr int XSLOTS = PASN_XSLOTS, WSLOTS = PASN_WSLOTS, XDEPTH = XSLOTS - 1;   // XDEPTH chunks of cp.async in flight per producer warp
 constexpr uint32_t XSLOT_BYTES = 16384, WSLOT_BYTES = 32768;
 constexpr int K1_WARPS = 16, K1_THREADS = K1_WARPS * 32;
 constexpr int W_MMA = 0, W_WPROD = 1, W_TAIL = 2, W_OCC = 3, W_X0 = 4, W_EPI0 = 8;
@@ -44,10 +47,10 @@ constexpr uint32_t SM_BIAS = SM_OS + OS_BYTES_MAX;                // 188416  b3[
 constexpr uint32_t SM_BAR = SM_BIAS + (DD + DD + DH) * 4;         // 190976
 constexpr uint32_t SM_MISC = SM_BAR + 36 * 8;                     // 191232
 constexpr uint32_t K1_SMEM = SM_MISC + 64;                        // 191296
-static_assert(PASN_XSLOTS != 4 || K1_SMEM <= 195 * 1024, "keep the 196 KB carve-out (60 KB of L1 for the cp.async gather)");
+static_assert(PASN_XSLOTS != 4 || PASN_WSLOTS != 3 || K1_SMEM <= 195 * 1024, "keep the 196 KB carve-out (60 KB of L1 for the cp.async gather)");
 
 enum {
-  B_XFULL = 0, B_XEMPTY = XSLOTS, B_WFULL = 2 * XSLOTS, B_WEMPTY = 2 * XSLOTS + 3, B_GDONE = 2 * XSLOTS + 6, B_ADONE, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
+  B_XFULL = 0, B_XEMPTY = XSLOTS, B_WFULL = 2 * XSLOTS, B_WEMPTY = 2 * XSLOTS + WSLOTS, B_GDONE = 2 * XSLOTS + 2 * WSLOTS, B_ADONE, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
   B_OSREADY, B_OSEMPTY, B_H1TREADY, B_FEDONE0, B_FEFREE0, B_FEDONE1, B_GBFREE, B_ABFREE, B_W4RDY, B_W5RDY, B_COUNT
 };
 static_assert(B_COUNT <= 36, "barrier table");
