@@ -131,6 +131,23 @@ int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packe
 int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dims* dims, void* occurrence_map,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of the head (training: loss.backward() through Video_XProtoNet.forward, src/agents/XProtoNet_Base.py:397,
+ * src/agents/Video_XProtoNet_e2e.py:138).  fp32 CUDA-core path; forward intermediates are recomputed, nothing has
+ * to be saved by the forward call.  Gradients of the fp32 formulation on the given inputs (a bf16 feature map is read
+ * exactly, weights are not rounded); sub-gradients as in PyTorch (relu'(0) = 0, d|x|/dx(0) = 0, clamped norms constant).
+ *   grad_logits      [N,K] fp32 or NULL     grad_similarity [N,P] fp32 or NULL     grad_occurrence [N,P,S] fp32 or NULL
+ *   grads            every pointer non-NULL, same shapes as pasn_weights; gradients are ADDED to the buffers
+ *   grad_feat        [N,C,S] fp32 (always channel-major, whatever dims.layout says about feat), or NULL           */
+typedef struct {
+  float* addon_w1; float* addon_b1; float* addon_w2; float* addon_b2;
+  float* occ_w1; float* occ_b1; float* occ_w2; float* occ_b2; float* occ_w3;
+  float* prototypes; float* last_layer;
+} pasn_grads;
+size_t pasn_head_backward_workspace_bytes(const pasn_dims* dims);
+int pasn_head_backward(const void* feat, const pasn_weights* w, const pasn_dims* dims, const float* grad_logits,
+                       const float* grad_similarity, const float* grad_occurrence, const pasn_grads* grads,
+                       float* grad_feat, void* workspace, size_t workspace_bytes, void* stream);
+
 /* push bookkeeping (src/utils/push_abs_revision.py:242, :299-300, :342-346) */
 int pasn_push_init(uint64_t* best_key, int32_t P, void* stream);          /* best_key[:] = +inf / no index */
 int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* index[p] = winner or -1       */

@@ -24,6 +24,7 @@ SYMBOLS = [
     "pasn_push_init", "pasn_push_decode", "pasn_push_select", "pasn_push_collect", "pasn_push_write_prototypes",
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
     "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant",
+    "pasn_head_backward_workspace_bytes", "pasn_head_backward",
 ]
 
 
@@ -35,6 +36,10 @@ class PasnWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "addon_w1", "addon_b1", "addon_w2", "addon_b2", "occ_w1", "occ_b1", "occ_w2", "occ_b2", "occ_w3",
         "prototypes", "last_layer")]
+
+
+class PasnGrads(C.Structure):
+    _fields_ = PasnWeights._fields_
 
 
 class PasnPushArgs(C.Structure):
@@ -92,6 +97,11 @@ def load() -> C.CDLL:
     lib.pasn_debug_last_main_kernel_ms.restype = C.c_float
     lib.pasn_debug_set_trace.restype = C.c_int
     lib.pasn_debug_set_trace.argtypes = [vp]
+    lib.pasn_head_backward_workspace_bytes.restype = C.c_size_t
+    lib.pasn_head_backward_workspace_bytes.argtypes = [C.POINTER(PasnDims)]
+    lib.pasn_head_backward.restype = C.c_int
+    lib.pasn_head_backward.argtypes = [vp, C.POINTER(PasnWeights), C.POINTER(PasnDims), vp, vp, vp, C.POINTER(PasnGrads),
+                                       vp, vp, C.c_size_t, vp]
     lib.pasn_debug_set_k1_variant.restype = C.c_int
     lib.pasn_debug_set_k1_variant.argtypes = [C.c_int]
     lib.pasn_debug_sm100_error.restype = C.c_int

@@ -47,6 +47,22 @@ extern "C" float pasn_debug_last_main_kernel_ms(void) {
   return ms;
 }
 
+extern "C" size_t pasn_head_backward_workspace_bytes(const pasn_dims* dims) {
+  return dims_ok(dims) ? backward_workspace_bytes(*dims) : 0;
+}
+extern "C" int pasn_head_backward(const void* feat, const pasn_weights* w, const pasn_dims* dims, const float* grad_logits,
+                                  const float* grad_similarity, const float* grad_occurrence, const pasn_grads* grads,
+                                  float* grad_feat, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dims_ok(dims) || !w || !grads) return PASN_ERR_INVALID;
+  if (dims->N == 0) return PASN_OK;
+  if (!feat || !workspace) return PASN_ERR_INVALID;
+  const float* const* gp = reinterpret_cast<const float* const*>(grads);
+  for (int i = 0; i < 11; ++i)
+    if (!gp[i]) return PASN_ERR_INVALID;
+  return head_backward(feat, *w, *dims, grad_logits, grad_similarity, grad_occurrence, *grads, grad_feat, workspace,
+                       workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream) {
   if (!workspace || !dims_ok(dims) || !sm100_supported(*dims)) return 0;
   return sm100_last_error(workspace, *dims, (cudaStream_t)stream);

@@ -62,6 +62,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- generic path (generic.cu) -------------------------------------------------------------
 size_t generic_workspace_bytes(const pasn_dims& d);
+size_t backward_workspace_bytes(const pasn_dims& d);
+int head_backward(const void* feat, const pasn_weights& w, const pasn_dims& d, const float* gLogits, const float* gSim,
+                  const float* gOcc, const pasn_grads& g, float* gX, void* ws, size_t ws_bytes, cudaStream_t st);
 int generic_head_forward(const void* feat, const pasn_weights& w, const pasn_dims& d, float* logits, float* sim,
                          void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws, size_t ws_bytes,
                          cudaStream_t st);

@@ -773,9 +773,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       }
     }
   } else if (warp == 8) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (one elected thread, lean issue path:
+    // see head_sm100_k1.cu -- descriptors as 32-bit halves in a single-thread region keep the UTCHMMAs back to back)
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, 256, 1, 0);  // A (pooled vectors) MN-major, B (W2) K-major
+      constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
+      const uint32_t bar0 = smem_u32(bars);
       uint32_t u = 0;
       bool ok = true;
       for (int it = 0; it < my_tiles && ok; ++it) {
@@ -785,17 +788,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
         for (int kc = 0; kc < 4 && ok; ++kc, ++u) {
           const uint32_t s = u & 1, ph = (u >> 1) & 1;
           if (!(ok = bwait(&bars[s], ph, ctx, 622))) break;
-          tc_fence_after();
           const uint32_t sb = st_base + s * K2_STAGE;
+          const uint32_t ah = desc_lo(sb, 8192), al = desc_lo(sb + 16384, 8192), bd = desc_lo(sb + 32768, 16);
+          const uint32_t d = tbase + 256u * buf;
+          mma_ss_x(d, ah, HI, bd, HI, idesc, kc ? 1u : 0u);
+          mma_ss_x(d, al, HI, bd, HI, idesc, 1u);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t bd = make_smem_desc(sb + 32768 + k4 * 32, 16, 1024, SWZ_128B);
-            const uint64_t ah = make_smem_desc(sb + k4 * 2048, 8192, 1024, SWZ_128B);
-            const uint64_t al = make_smem_desc(sb + 16384 + k4 * 2048, 8192, 1024, SWZ_128B);
-            mma_ss(tbase + 256u * buf, ah, bd, idesc, (kc | k4) ? 1u : 0u);
-            mma_ss(tbase + 256u * buf, al, bd, idesc, 1u);
+          for (int k4 = 1; k4 < 4; ++k4) {
+            mma_ss_x(d, ah + k4 * 128, HI, bd + k4 * 2, HI, idesc, 1u);
+            mma_ss_x(d, al + k4 * 128, HI, bd + k4 * 2, HI, idesc, 1u);
           }
-          mma_commit(&bars[2 + s]);
+          mma_commit_a(bar0 + 8u * (2 + s));
         }
         if (ok) mma_commit(&bars[4 + buf]);
       }

@@ -10,9 +10,10 @@ Reference interface being mirrored (paths relative to the reference checkout):
 
 The backbone stays PyTorch (north_star); everything from its feature map to the logits runs in the CUDA
 library.  There is NO PyTorch/CPU fallback for inference: a CPU tensor, or a missing library, raises.
-Training through the head (autograd) is not implemented in the kernels yet (SURVEY.md section 8f row 2);
-``autograd_mode='composite'`` opts in, explicitly, to a differentiable PyTorch composite of the same maths
-on the GPU for ``requires_grad`` calls -- the default ``'error'`` refuses instead of silently switching.
+Training through the head: ``autograd_mode='kernel'`` runs ``requires_grad`` calls
+through the library as well (forward as usual, backward = ``pasn_head_backward``, fp32 CUDA-core kernels that
+recompute the forward intermediates); ``'composite'`` opts in to a differentiable PyTorch composite of the same maths
+on the GPU; the default ``'error'`` refuses instead of silently switching.
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import PasnDims, PasnPushArgs, PasnWeights
+from ._lib import PasnDims, PasnGrads, PasnPushArgs, PasnWeights
 
 
 import os as _os
@@ -153,6 +154,58 @@ class _HeadRuntime:
         return occ
 
 
+class _HeadFunction(torch.autograd.Function):
+    """(features, 11 head parameters) -> (logits, similarity, occurrence_map): forward through the library's usual path,
+    backward through ``pasn_head_backward`` (fp32 CUDA-core kernels, forward intermediates recomputed)."""
+
+    @staticmethod
+    def forward(ctx, rt, x, *params):
+        with torch.no_grad():
+            r = rt.run(x, want_occ=True)
+        ctx.rt = rt
+        ctx.save_for_backward(x, *params)
+        return r["logits"], r["similarity"], r["occurrence_map"]
+
+    @staticmethod
+    def backward(ctx, g_logits, g_sim, g_occ):
+        x, *params = ctx.saved_tensors
+        rt = ctx.rt
+        lib = _lib.load()
+        m = rt.owner
+        dims, xc, spatial = rt.make_dims(x, _lib.PASN_PATH_GENERIC)
+        dev = xc.device
+        with torch.cuda.device(dev), torch.no_grad():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            w, tensors = rt._weights_struct(m)
+            grads = [torch.zeros_like(t) for t in tensors]
+            gw = PasnGrads(*[g.data_ptr() for g in grads])
+            want_gx = ctx.needs_input_grad[1]
+            gx = torch.empty((dims.N, dims.C, dims.S), dtype=torch.float32, device=dev) if want_gx else None
+
+            def prep(g, shape):
+                if g is None:
+                    return None
+                return g.to(torch.float32).reshape(shape).contiguous()
+
+            gl = prep(g_logits, (dims.N, dims.K))
+            gs = prep(g_sim, (dims.N, dims.P))
+            go = prep(g_occ, (dims.N, dims.P, dims.S))
+            if dims.N > 0:
+                need = int(lib.pasn_head_backward_workspace_bytes(C.byref(dims)))
+                ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+                st = lib.pasn_head_backward(xc.data_ptr(), C.byref(w), C.byref(dims), _ptr(gl), _ptr(gs), _ptr(go),
+                                            C.byref(gw), _ptr(gx), ws.data_ptr(), ws.numel(), stream)
+                _lib.check(st, "pasn_head_backward")
+            elif gx is not None:
+                gx.zero_()
+        if gx is not None:
+            gx = gx.reshape((dims.N, dims.C) + spatial).to(x.dtype)
+        out = [None, gx]
+        for i, t in enumerate(tensors):
+            out.append(grads[i].reshape(params[i].shape) if ctx.needs_input_grad[2 + i] else None)
+        return tuple(out)
+
+
 def get_prototype_class_identity(num_prototypes: int, num_classes: int) -> torch.Tensor:
     """One-hot (P, K), prototype j -> class j // (P/K).  Reference: src/models/ProtoPNet.py:326-340."""
     assert num_prototypes % num_classes == 0
@@ -196,7 +249,7 @@ class PrototypeHeadMixin:
     """forward / push_forward / compute_occurence_map shared by the video and image models."""
 
     kernel_path: int = _lib.PASN_PATH_AUTO   # PASN_PATH_* selector (AUTO: tcgen05 when the shape qualifies)
-    autograd_mode: str = "error"             # 'error' | 'composite'
+    autograd_mode: str = "error"             # 'error' | 'kernel' | 'composite'
 
     def _init_head(self, cnn_backbone, img_size, prototype_shape, proto_layer_rf_info, num_classes, init_weights, conv):
         self.img_size = img_size
@@ -261,19 +314,28 @@ class PrototypeHeadMixin:
 
     def _grad_guard(self, x):
         if self._needs_grad(x):
-            if self.autograd_mode == "composite":
+            if self.autograd_mode in ("composite", "kernel"):
                 return True
             raise NotImplementedError(
-                "protoasnet_b200: the CUDA prototype head is forward-only. Call under torch.no_grad() "
-                "(eval / push / explain), or set model.autograd_mode = 'composite' to train through an explicit "
-                "PyTorch composite of the head.")
+                "protoasnet_b200: this call needs gradients. Call under torch.no_grad() (eval / push / explain), or set "
+                "model.autograd_mode = 'kernel' (backward through the library) or 'composite' (explicit PyTorch "
+                "composite of the head) to train.")
         return False
+
+    def _kernel_autograd(self, x):
+        """(logits, similarity, occurrence_map) with gradients flowing through pasn_head_backward."""
+        a, o = self.add_on_layers, self.occurrence_module
+        params = (a[0].weight, a[0].bias, a[2].weight, a[2].bias, o[0].weight, o[0].bias, o[2].weight, o[2].bias,
+                  o[4].weight, self.prototype_vectors, self.last_layer.weight)
+        return _HeadFunction.apply(self._rt, x, *params)
 
     # ---- reference API ----
     def forward(self, x):
         """-> (logits [N,K], similarity [N,P], occurrence_map [N,P,1,(T),H,W]).  Video_XProtoNet.py:82-98."""
         x = self.cnn_backbone(x)
         if self._grad_guard(x):
+            if self.autograd_mode == "kernel":
+                return self._kernel_autograd(x)
             _, sim, occ, logits = self._composite(x)
             return logits, sim, occ
         r = self._rt.run(x, want_occ=True)
