@@ -148,6 +148,22 @@ int pasn_head_backward(const void* feat, const pasn_weights* w, const pasn_dims*
                        const float* grad_similarity, const float* grad_occurrence, const pasn_grads* grads,
                        float* grad_feat, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Loss / metric consumers of the head outputs, on the device (no per-step host round trip):
+ *   class_max[n,k] / class_arg[n,k]  max (and global prototype index of the first maximum) of similarity over the
+ *                                    prototypes of class k (P/K consecutive prototypes per class)
+ *   sums[0] += -sum_n class_max[n, labels[n]]                           ClusterRoiFeat,    src/loss/loss.py:114-138
+ *   sums[1] += sum_n sum_{k != labels[n], k != K-1 if abstain} class_max[n,k]   SeparationRoiFeat, src/loss/loss.py:158-187
+ *   counts[j] += [j among the top_specific most similar prototypes of [0,n_specific)] + [... top_rest of the rest]
+ *   sim_cumsum[j] += sum_n similarity[n,j]                              src/agents/Video_XProtoNet_e2e.py:158-173
+ * Any output may be NULL; labels may be NULL when sums is NULL.  P <= 64 when counts is given. */
+int pasn_similarity_stats(const float* similarity, const int64_t* labels, int32_t N, int32_t P, int32_t K, int32_t abstain,
+                          int32_t n_specific, int32_t top_specific, int32_t top_rest, float* class_max, int32_t* class_arg,
+                          double* sums, uint64_t* counts, double* sim_cumsum, void* stream);
+/* sum[0] += sum over rows of ||occ[row, 0:S]||_p (p = 1 or 2; L_norm over the spatial dims, src/loss/loss.py:236-250);
+ * row_norm[row] = that norm (or NULL).  occ is [rows][S] in `dtype`. */
+int pasn_occurrence_lnorm(const void* occ, int32_t dtype, int64_t rows, int32_t S, int32_t p, double* sum, float* row_norm,
+                          void* stream);
+
 /* push bookkeeping (src/utils/push_abs_revision.py:242, :299-300, :342-346) */
 int pasn_push_init(uint64_t* best_key, int32_t P, void* stream);          /* best_key[:] = +inf / no index */
 int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* index[p] = winner or -1       */

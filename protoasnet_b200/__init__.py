@@ -8,7 +8,8 @@ from .head import (MODELS, FeatureInput, Video_XProtoNet, XProtoNet, build, cons
                    construct_XProtoNet)
 from .push import push_prototypes, push_resident  # noqa: F401
 from .explain import collect_model_products, load_data_and_model_products  # noqa: F401
+from . import metrics  # noqa: F401
 
 __all__ = ["MODELS", "FeatureInput", "Video_XProtoNet", "XProtoNet", "build", "construct_Video_XProtoNet",
            "construct_XProtoNet", "push_prototypes", "push_resident", "collect_model_products",
-           "load_data_and_model_products"]
+           "load_data_and_model_products", "metrics"]

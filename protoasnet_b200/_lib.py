@@ -24,7 +24,7 @@ SYMBOLS = [
     "pasn_push_init", "pasn_push_decode", "pasn_push_select", "pasn_push_collect", "pasn_push_write_prototypes",
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
     "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant",
-    "pasn_head_backward_workspace_bytes", "pasn_head_backward",
+    "pasn_head_backward_workspace_bytes", "pasn_head_backward", "pasn_similarity_stats", "pasn_occurrence_lnorm",
 ]
 
 
@@ -102,6 +102,11 @@ def load() -> C.CDLL:
     lib.pasn_head_backward.restype = C.c_int
     lib.pasn_head_backward.argtypes = [vp, C.POINTER(PasnWeights), C.POINTER(PasnDims), vp, vp, vp, C.POINTER(PasnGrads),
                                        vp, vp, C.c_size_t, vp]
+    lib.pasn_similarity_stats.restype = C.c_int
+    lib.pasn_similarity_stats.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          vp, vp, vp, vp, vp, vp]
+    lib.pasn_occurrence_lnorm.restype = C.c_int
+    lib.pasn_occurrence_lnorm.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]
     lib.pasn_debug_set_k1_variant.restype = C.c_int
     lib.pasn_debug_set_k1_variant.argtypes = [C.c_int]
     lib.pasn_debug_sm100_error.restype = C.c_int

@@ -47,6 +47,23 @@ extern "C" float pasn_debug_last_main_kernel_ms(void) {
   return ms;
 }
 
+extern "C" int pasn_similarity_stats(const float* similarity, const int64_t* labels, int32_t N, int32_t P, int32_t K,
+                                     int32_t abstain, int32_t n_specific, int32_t top_specific, int32_t top_rest,
+                                     float* class_max, int32_t* class_arg, double* sums, uint64_t* counts,
+                                     double* sim_cumsum, void* stream) {
+  if (N < 0 || P <= 0 || K <= 0 || (sums && !labels)) return PASN_ERR_INVALID;
+  if (N > 0 && !similarity) return PASN_ERR_INVALID;
+  return launch_sim_stats(similarity, labels, N, P, K, abstain, n_specific, top_specific, top_rest, class_max, class_arg,
+                          sums, reinterpret_cast<unsigned long long*>(counts), sim_cumsum,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int pasn_occurrence_lnorm(const void* occ, int32_t dtype, int64_t rows, int32_t S, int32_t p, double* sum,
+                                     float* row_norm, void* stream) {
+  if (rows < 0 || S <= 0 || !sum || (rows > 0 && !occ)) return PASN_ERR_INVALID;
+  if (dtype != PASN_F32 && dtype != PASN_BF16) return PASN_ERR_INVALID;
+  return launch_occ_lnorm(occ, dtype, rows, S, p, sum, row_norm, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" size_t pasn_head_backward_workspace_bytes(const pasn_dims* dims) {
   return dims_ok(dims) ? backward_workspace_bytes(*dims) : 0;
 }
