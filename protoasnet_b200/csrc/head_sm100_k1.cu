@@ -297,17 +297,31 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           if (!(ok = bwait(&bars[B_ABFREE], tp ^ 1, ctx, 111))) break;
           tc_fence_after();
           stamp(tile, 3);
-          for (int kc = 0; kc < nkc && ok; ++kc) {
+          // (G, A) blocks per chunk, except that the last `skew` chunks issue their G blocks first: acc_G is then
+          // complete -- and G1's conversion can start -- while the add-on blocks of those chunks are still running
+          // (their X slots stay held a little longer; at the end of a tile the ring has nothing urgent to prefetch)
+          // skew <= XSLOTS - (XDEPTH - 1): a chunk is only published once the XDEPTH - 1 chunks after it were issued,
+          // and those need free slots while this thread still holds `skew` of them
+          constexpr int SKEW = XSLOTS - (XDEPTH - 1) < 3 ? XSLOTS - (XDEPTH - 1) : 3;
+          // (only for channels_last input: the NCDHW gather is the slower one and does not like waiting for two chunks
+          // before the add-on block of the first -- measured 159.6 vs 157.3 us -- while channels_last gains 2-4 %)
+          const int skew = !p.nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
+          for (int kc = 0; kc < k_skew && ok; ++kc) {
             long long tc0 = 0;
             if constexpr (TRACE) tc0 = clock64();
             uint32_t sx;
             ok = take_x(sx) && chunk_g(kc, sx, false) && chunk_a(kc, sx);
             chunk_time(tile, kc, tc0);
           }
+          uint32_t sxs[3] = {0, 0, 0};
+          for (int j = 0; j < skew && ok; ++j) ok = take_x(sxs[j]) && chunk_g(k_skew + j, sxs[j], false);
           if (!ok) break;
           mma_commit_a(baddr(B_GDONE));
-          mma_commit_a(baddr(B_ADONE));
           stamp(tile, 2);
+          for (int j = 0; j < skew && ok; ++j) ok = chunk_a(k_skew + j, sxs[j]);
+          if (!ok) break;
+          mma_commit_a(baddr(B_ADONE));
+          stamp(tile, 6);
           ok = pass_w(2, B_W4RDY) && pass_w(1, B_W5RDY);
         }
         if constexpr (TRACE) {
@@ -398,7 +412,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   } else if (warp == W_WPROD) {
     // ------------------------------------------------------------------ weight producer (one thread)
     // stage order = consumption order of the issuer.  two-phase: W3[0..nkc), then W1[0..nkc) with W4a,W4b before
-    // chunk a1 and W5 before chunk a2.  single-phase: (W3[k], W1[k]) pairs, W4a, W4b, W5.
+    // chunk a1 and W5 before chunk a2.  single-phase: (W3[k], W1[k]) pairs, for the
+    // last two chunks all W3 before all W1 (skewed issue order), then W4a, W4b, W5.
     if (lane == 0) {
       uint32_t wst = 0;
       bool ok = true;
@@ -421,8 +436,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
             if (ok) ok = put(PL.off_l1 + (size_t)(2 * kc + 1) * 32768, 32768);
           }
         } else {
-          for (int kc = 0; kc < nkc && ok; ++kc)
+          constexpr int SKEW = XSLOTS - (XDEPTH - 1) < 3 ? XSLOTS - (XDEPTH - 1) : 3;
+          const int skew = !p.nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
+          for (int kc = 0; kc < k_skew && ok; ++kc)
             ok = put(PL.off_l1 + (size_t)(2 * kc) * 32768, 32768) && put(PL.off_l1 + (size_t)(2 * kc + 1) * 32768, 32768);
+          for (int kc = k_skew; kc < nkc && ok; ++kc) ok = put(PL.off_l1 + (size_t)(2 * kc) * 32768, 32768);
+          for (int kc = k_skew; kc < nkc && ok; ++kc) ok = put(PL.off_l1 + (size_t)(2 * kc + 1) * 32768, 32768);
           ok = ok && put(PL.off_w4, 32768) && put(PL.off_w4 + 32768, 32768) && put(PL.off_w5, 16384);
         }
       }
