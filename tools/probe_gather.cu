@@ -170,6 +170,79 @@ static void run_cp(const char* name, const __nv_bfloat16* feat, int N, long long
   if (e != cudaSuccess) exit(2);
 }
 
+
+// MODE 2: clean mixed gather.  Per channel row and clip segment, rows whose source is 16-byte aligned at even piece
+// indices use one 16-byte cp.async.cg per lane pair (issued by the even lane, bypasses L1); everything else 8-byte .ca.
+template <int NW, int DEPTH>
+__global__ void __launch_bounds__(NW * 32) gather_mixed_kernel(const __nv_bfloat16* __restrict__ feat, int N, int clips_per_cta,
+                                                                long long* cycles, unsigned* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c_begin = blockIdx.x * clips_per_cta;
+  int ncl = min(N - c_begin, clips_per_cta);
+  if (ncl <= 0) return;
+  const int ntok = ncl * S, ntiles = (ntok + TILE_M - 1) / TILE_M;
+  constexpr int RPW = 64 / NW;
+  const uint32_t x_base = smem_u32(smem);
+  const int njobs = ntiles * NKC;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int job = 0; job < njobs; ++job) {
+    const int tile = job / NKC, kc = job % NKC;
+    const uint32_t dst0 = x_base + (job & 3) * 16384;
+    const int t = tile * TILE_M + 4 * lane;
+    const bool valid = t < ntok;
+    const int clipl = valid ? t / S : 0, s = valid ? t - clipl * S : 0;
+    // partner piece (lane ^ 1) in the same clip and valid?  (pieces are 4 voxels; S % 4 == 0)
+    const int tp = tile * TILE_M + 4 * (lane | 1);
+    const bool pair_ok = valid && tp < ntok && (tp / S) == clipl && ((lane & 1) == 0 ? true : true);
+    const __nv_bfloat16* src = feat + ((size_t)(c_begin + clipl) * C + kc * 64 + warp * RPW) * S + s;
+    // alignment of this lane's piece for row j: ((rowg + s/4) & 1) == 0 -> 16-byte aligned
+    const int par0 = (((c_begin + clipl) * C + kc * 64 + warp * RPW) + (s >> 2)) & 1;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+      const bool piece_aligned = ((par0 + j) & 1) == 0;   // S odd multiple of 4: alternates with the row index
+      const uint32_t dst = dst0 + off_mnmajor_sw128(4 * lane, warp * RPW + j, 8192);
+      // even lane with an aligned piece and a good partner: one 16-byte copy for both pieces; its partner issues nothing
+      const bool lead16 = (lane & 1) == 0 && piece_aligned && pair_ok;
+      const bool covered = (lane & 1) == 1 && !piece_aligned && pair_ok;   // partner (even lane) is aligned and copies for us
+      if (lead16) cp_async_16(dst, src + (size_t)j * S, 16u);
+      else if (!covered) cp_async_8(dst, src + (size_t)j * S, valid ? 8u : 0u);
+    }
+    cp_async_commit();
+    cp_async_wait<DEPTH - 1>();
+    if (((job + 1) & 3) == 0) fence_proxy_async();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (sink != nullptr && smem[threadIdx.x * 16] == 0x5a) atomicAdd(sink, 1u);
+}
+
+template <int NW, int DEPTH>
+static void run_mixed(const char* name, const __nv_bfloat16* feat, int N, long long* d_cyc, unsigned* d_sink, int smem_kb) {
+  auto k = gather_mixed_kernel<NW, DEPTH>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
+  const int cpc = (N + 147) / 148, grid = (N + cpc - 1) / cpc;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i) k<<<grid, NW * 32, smem_kb * 1024>>>(feat, N, cpc, d_cyc, d_sink);
+  cudaEventRecord(e0);
+  for (int i = 0; i < 5; ++i) k<<<grid, NW * 32, smem_kb * 1024>>>(feat, N, cpc, d_cyc, d_sink);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  long long h[148];
+  cudaMemcpy(h, d_cyc, sizeof h, cudaMemcpyDeviceToHost);
+  const double us = ms * 1e3 / 5, bytes = (double)N * C * S * 2;
+  const int tiles = (cpc * S + 127) / 128;
+  printf("%-58s smem %3d KB: %7.1f us  %6.0f GB/s  CTA0 %.0f cyc/chunk (%.1f B/clk/SM)  %s\n", name, smem_kb, us,
+         bytes / us * 1e-3, (double)h[0] / (tiles * NKC), 16384.0 * tiles * NKC / h[0], cudaGetErrorString(e));
+  if (e != cudaSuccess) exit(2);
+}
+
 template <int NW, int ROWS, int DEPTH, int ALLOC_L1, int REPEAT>
 static void run(const char* name, const __nv_bfloat16* feat, int N, long long* d_cyc, unsigned* d_sink, int smem_kb) {
   auto k = gather_kernel<NW, ROWS, DEPTH, ALLOC_L1, REPEAT>;
@@ -216,5 +289,8 @@ int main() {
   run_cp<4, 3, 0, 2>("cp.async.ca 8 B, 4 warps, 3 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
   run_cp<4, 4, 0, 2>("cp.async.ca 8 B, 4 warps, 4 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
   run_cp<8, 3, 0, 2>("cp.async.ca 8 B, 8 warps, 3 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
+  run_mixed<4, 3>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 3 groups", feat, N, d_cyc, d_sink, 187);
+  run_mixed<4, 3>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 3 groups", feat, N, d_cyc, d_sink, 219);
+  run_mixed<4, 4>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 4 groups", feat, N, d_cyc, d_sink, 219);
   return 0;
 }
