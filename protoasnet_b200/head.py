@@ -206,6 +206,66 @@ class _HeadFunction(torch.autograd.Function):
         return tuple(out)
 
 
+class HostPipeline:
+    """Head forward for batches that live in pinned host memory: the batch is cut into ``chunks`` pieces, each piece's
+    host->device copy runs on a copy stream while the previous piece is in the kernels, and logits / similarities
+    (optionally occurrence maps) go back into pinned host buffers.  Device staging and host result buffers are
+    allocated once and reused, so a steady-state call does no allocation.  The step then costs about one H2D copy of
+    the batch instead of copy + compute.
+
+        pipe = HostPipeline(model, chunks=4)
+        logits, sim = pipe(x_host_pinned)          # pinned host tensors, valid until the next call
+    """
+
+    def __init__(self, model, chunks: int = 4, device=None, want_occ: bool = False):
+        self.model, self.chunks, self.want_occ = model, max(1, int(chunks)), want_occ
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._stage = None
+        self._host = None
+
+    @torch.no_grad()
+    def __call__(self, x_host: torch.Tensor):
+        m, dev = self.model, self.device
+        n = int(x_host.shape[0])
+        bounds = [(i * n) // self.chunks for i in range(self.chunks + 1)]
+        pieces = [(bounds[i], bounds[i + 1]) for i in range(self.chunks) if bounds[i + 1] > bounds[i]]
+        cmax = max((b - a for a, b in pieces), default=0)
+        key = (tuple(x_host.shape[1:]), x_host.dtype, cmax, n)
+        if self._stage is None or self._stage[0] != key:
+            bufs = [torch.empty((cmax,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=dev) for _ in range(2)]
+            self._stage = (key, bufs)
+            P, K = int(m.prototype_shape[0]), int(m.num_classes)
+            host = {"logits": torch.empty((n, K), dtype=torch.float32).pin_memory(),
+                    "similarity": torch.empty((n, P), dtype=torch.float32).pin_memory()}
+            if self.want_occ:
+                host["occurrence_map"] = torch.empty((n, P, 1) + tuple(x_host.shape[2:]), dtype=x_host.dtype).pin_memory()
+            self._host = host
+        bufs, host = self._stage[1], self._host
+        main = torch.cuda.current_stream(dev)
+        free = [None, None]      # event: kernels that read staging buffer i are done
+        for i, (a, b) in enumerate(pieces):
+            buf = bufs[i & 1][: b - a]
+            with torch.cuda.stream(self.copy_stream):
+                if free[i & 1] is not None:
+                    self.copy_stream.wait_event(free[i & 1])
+                buf.copy_(x_host[a:b], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+            main.wait_event(ready)
+            logits, sim, occ = m(buf)
+            host["logits"][a:b].copy_(logits, non_blocking=True)
+            host["similarity"][a:b].copy_(sim, non_blocking=True)
+            if self.want_occ:
+                host["occurrence_map"][a:b].copy_(occ, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            free[i & 1] = done
+        if self.want_occ:
+            return host["logits"], host["similarity"], host["occurrence_map"]
+        return host["logits"], host["similarity"]
+
+
 def get_prototype_class_identity(num_prototypes: int, num_classes: int) -> torch.Tensor:
     """One-hot (P, K), prototype j -> class j // (P/K).  Reference: src/models/ProtoPNet.py:326-340."""
     assert num_prototypes % num_classes == 0
