@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NW * 32) gather_kernel(const __nv_bfloat16* __
 
 // cp.async (LDGSTS) variant: no registers, DEPTH commit groups in flight per warp.  MODE 0: 8-byte .ca copies for every
 // row; MODE 1: rows whose global address is 16-byte aligned use 16-byte .cg copies (two rows per warp instruction).
-template <int NW, int DEPTH, int MODE, int REPEAT = 1>
+template <int NW, int DEPTH, int MODE, int REPEAT = 1, int FENCE_EVERY = 4>
 __global__ void __launch_bounds__(NW * 32) gather_cp_kernel(const __nv_bfloat16* __restrict__ feat, int N, int clips_per_cta,
                                                              long long* cycles, unsigned* sink) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NW * 32) gather_cp_kernel(const __nv_bfloat16*
     }
     cp_async_commit();
     cp_async_wait<DEPTH - 1>();
-    if (((job + 1) & 3) == 0) fence_proxy_async();
+    if (FENCE_EVERY > 0 && ((job + 1) % FENCE_EVERY) == 0) fence_proxy_async();
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(NW * 32) gather_cp_kernel(const __nv_bfloat16*
   if (sink != nullptr && smem[threadIdx.x * 16] == 0x5a) atomicAdd(sink, 1u);
 }
 
-template <int NW, int DEPTH, int MODE, int REPEAT = 1>
+template <int NW, int DEPTH, int MODE, int REPEAT = 1, int FENCE_EVERY = 4>
 static void run_cp(const char* name, const __nv_bfloat16* feat, int N, long long* d_cyc, unsigned* d_sink, int smem_kb) {
-  auto k = gather_cp_kernel<NW, DEPTH, MODE, REPEAT>;
+  auto k = gather_cp_kernel<NW, DEPTH, MODE, REPEAT, FENCE_EVERY>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024);
   const int cpc = (N + 147) / 148, grid = (N + cpc - 1) / cpc;
   cudaEvent_t e0, e1;
@@ -275,22 +275,10 @@ int main() {
   cudaMemset(feat, 0, (size_t)N * C * S * 2);
   cudaMalloc(&d_cyc, 148 * 8); cudaMalloc(&d_sink, 4);
   cudaMemset(d_sink, 0, 4);
-  run<4, 16, 2, 0, 1>("LDG 4 warps, 16-row units, depth 2 (current)", feat, N, d_cyc, d_sink, 224);
-  run_cp<4, 2, 0>("cp.async.ca 8 B, 4 warps, 2 groups", feat, N, d_cyc, d_sink, 224);
-  run_cp<4, 2, 0>("cp.async.ca 8 B, 4 warps, 2 groups", feat, N, d_cyc, d_sink, 195);
-  run_cp<4, 3, 0>("cp.async.ca 8 B, 4 warps, 3 groups", feat, N, d_cyc, d_sink, 195);
-  run_cp<4, 4, 0>("cp.async.ca 8 B, 4 warps, 4 groups", feat, N, d_cyc, d_sink, 195);
-  run_cp<4, 3, 0>("cp.async.ca 8 B, 4 warps, 3 groups", feat, N, d_cyc, d_sink, 187);
-  run_cp<8, 3, 0>("cp.async.ca 8 B, 8 warps, 3 groups", feat, N, d_cyc, d_sink, 187);
-  run_cp<2, 3, 0>("cp.async.ca 8 B, 2 warps, 3 groups", feat, N, d_cyc, d_sink, 187);
-  run_cp<4, 3, 0>("cp.async.ca 8 B, 4 warps, 3 groups", feat, N, d_cyc, d_sink, 163);
-  run_cp<4, 3, 0>("cp.async.ca 8 B, 4 warps, 3 groups", feat, N, d_cyc, d_sink, 131);
-  run_cp<4, 2, 0, 2>("cp.async.ca 8 B, 4 warps, 2 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
-  run_cp<4, 3, 0, 2>("cp.async.ca 8 B, 4 warps, 3 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
-  run_cp<4, 4, 0, 2>("cp.async.ca 8 B, 4 warps, 4 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
-  run_cp<8, 3, 0, 2>("cp.async.ca 8 B, 8 warps, 3 groups, every chunk twice", feat, N, d_cyc, d_sink, 187);
-  run_mixed<4, 3>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 3 groups", feat, N, d_cyc, d_sink, 187);
-  run_mixed<4, 3>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 3 groups", feat, N, d_cyc, d_sink, 219);
-  run_mixed<4, 4>("mixed 16 B .cg / 8 B .ca (clean), 4 warps, 4 groups", feat, N, d_cyc, d_sink, 219);
+  run_cp<4, 3, 0, 1, 0>("cp.async.ca 8 B, 3 groups, no proxy fence", feat, N, d_cyc, d_sink, 187);
+  run_cp<4, 3, 0, 1, 4>("cp.async.ca 8 B, 3 groups, proxy fence every 4 chunks", feat, N, d_cyc, d_sink, 187);
+  run_cp<4, 3, 0, 1, 1>("cp.async.ca 8 B, 3 groups, proxy fence every chunk", feat, N, d_cyc, d_sink, 187);
+  run_cp<4, 3, 0, 2, 1>("same, every chunk twice", feat, N, d_cyc, d_sink, 187);
+  run_cp<4, 3, 0, 2, 0>("no fence, every chunk twice", feat, N, d_cyc, d_sink, 187);
   return 0;
 }
