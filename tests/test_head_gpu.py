@@ -318,3 +318,30 @@ def test_host_pipeline_matches_direct_forward():
     lg1, sm1 = pasn.HostPipeline(m, chunks=1)(xh)
     torch.cuda.synchronize()
     assert torch.equal(lg1, logits.cpu()) and torch.equal(sm1, sim.cpu())
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The C ABI neither allocates nor synchronises, so a forward call can be captured in a CUDA graph and replayed
+    (serving loops): same results as the eager call, on new input data copied into the captured buffer."""
+    dims = synth.CONFIGS["cfg3_video_b1024"]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    m = build_model(dims, sd)
+    x1 = torch.from_numpy(synth.make_features(dims, 33, seed=7, bf16_round=True)).cuda().bfloat16()
+    x2 = torch.from_numpy(synth.make_features(dims, 33, seed=8, bf16_round=True)).cuda().bfloat16()
+    static_x = x1.clone()
+    with torch.no_grad():
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):      # warm-up: function attributes, packed weights, workspace
+                m(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            logits, sim, occ = m(static_x)
+        for x in (x1, x2):
+            static_x.copy_(x)
+            g.replay()
+            torch.cuda.synchronize()
+            el, es, eo = m(x)
+            assert torch.equal(logits, el) and torch.equal(sim, es) and torch.equal(occ, eo)
