@@ -967,11 +967,59 @@ static inline int k2_ppad(const pasn_dims& d) {
   const int p8 = (d.P + 7) / 8 * 8;
   return p8 <= 16 ? 16 : p8 <= 32 ? 32 : p8 <= 40 ? 40 : 48;   // matches the head_tokens_kernel<PP> instantiations
 }
-static inline int k2_tiles(const pasn_dims& d) { return ceil_div(d.N, TILE_M / k2_ppad(d)); }
+// Small batches: one persistent CTA per clip range leaves most SMs idle when N < 148.  Pooling is linear in the voxels,
+// so a clip of S voxels can be processed as G independent "virtual clips" of S/G voxels (each at least one 128-voxel
+// tile, multiple of 4) whose pooled features are summed after K2.  G = 1 means no split.
+static inline int split_groups(const pasn_dims& d) {
+  if (d.N <= 0 || d.N > 74) return 1;
+  static const int allow = [] { const char* e = getenv("PASN_NO_SPLIT"); return (e && atoi(e) != 0) ? 0 : 1; }();
+  if (!allow) return 1;
+  int best = 1;
+  for (int g = 2; g <= d.S / TILE_M; ++g) {
+    if (d.S % g != 0) continue;
+    const int sv = d.S / g;
+    if (sv < TILE_M || sv % 4 != 0) continue;
+    if ((long long)d.N * g > 148) break;         // one virtual clip range per SM is enough; beyond that the extra
+                                                  // kernels of the split cost more than the parallelism gains
+    best = g;
+  }
+  return best;
+}
+struct WsLayout {
+  int G, Nv, Sv, tiles2;
+  size_t off_osum, off_err, off_featsv, off_fe, off_simv, off_logv, total;
+};
+static inline WsLayout ws_layout(const pasn_dims& d) {
+  WsLayout L;
+  L.G = split_groups(d);
+  L.Nv = d.N * L.G;
+  L.Sv = d.S / L.G;
+  L.tiles2 = ceil_div(L.Nv, TILE_M / k2_ppad(d));
+  size_t o = (size_t)L.tiles2 * FE_TILE_BYTES;
+  L.off_osum = o; o += align_up((size_t)L.Nv * d.P * 4, 256);
+  L.off_err = o; o += 256;
+  L.off_featsv = L.off_fe = L.off_simv = L.off_logv = o;
+  if (L.G > 1) {
+    L.off_featsv = o; o += align_up((size_t)L.Nv * d.P * DD * 4, 256);   // K2's features per virtual clip
+    L.off_fe = o; o += align_up((size_t)d.N * d.P * DD * 4, 256);        // their sum per real clip
+    L.off_simv = o; o += align_up((size_t)L.Nv * d.P * 4, 256);          // K2's per-virtual-clip similarity / logits: unused
+    L.off_logv = o; o += align_up((size_t)L.Nv * d.K * 4, 256);
+  }
+  L.total = o;
+  return L;
+}
 
-// workspace: K2 operand images [ntiles2][128 KB] | Osum [N][P] fp32 | err int
-size_t sm100_workspace_bytes(const pasn_dims& d) {
-  return (size_t)k2_tiles(d) * FE_TILE_BYTES + align_up((size_t)d.N * d.P * 4, 256) + 256;
+// workspace: K2 operand images [tiles2][128 KB] | Osum [Nv][P] fp32 | err int | (split only) scratch, see ws_layout
+size_t sm100_workspace_bytes(const pasn_dims& d) { return ws_layout(d).total; }
+
+// FE[n][i] = sum_g FEv[n*G + g][i]   (i over P*D)
+__global__ void sum_groups_kernel(const float* __restrict__ fev, float* __restrict__ fe, int N, int G, int PD) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * PD) return;
+  const long long n = i / PD, r = i - n * PD;
+  float a = 0.f;
+  for (int g = 0; g < G; ++g) a += fev[((size_t)n * G + g) * PD + r];
+  fe[i] = a;
 }
 
 int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, cudaStream_t st) {
@@ -1007,10 +1055,11 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
       return PASN_ERR_CUDA;
     attr_done = true;
   }
+  const WsLayout L = ws_layout(d);
   char* wsp = reinterpret_cast<char*>(ws);
   uint8_t* feimg = reinterpret_cast<uint8_t*>(wsp);
-  float* osum = reinterpret_cast<float*>(wsp + (size_t)k2_tiles(d) * FE_TILE_BYTES);
-  int* err = reinterpret_cast<int*>(reinterpret_cast<char*>(osum) + align_up((size_t)d.N * d.P * 4, 256));
+  float* osum = reinterpret_cast<float*>(wsp + L.off_osum);
+  int* err = reinterpret_cast<int*>(wsp + L.off_err);
   if (cudaMemsetAsync(err, 0, 4, st) != cudaSuccess) return PASN_ERR_CUDA;
 
   const int num_sms = 148;
@@ -1023,13 +1072,14 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.occ = k1.f32_in ? nullptr : reinterpret_cast<__nv_bfloat16*>(occ);
   k1.occ32 = k1.f32_in ? reinterpret_cast<float*>(occ) : nullptr;
   k1.feimg = feimg; k1.osum = osum;
-  k1.N = d.N; k1.C = d.C; k1.P = d.P; k1.S = d.S; k1.nkc = d.C / 64;
-  k1.clips_per_cta = ceil_div(d.N, num_sms);
+  k1.N = L.Nv; k1.C = d.C; k1.P = d.P; k1.S = L.Sv; k1.nkc = d.C / 64;
+  k1.G = L.G; k1.SR = d.S;
+  k1.clips_per_cta = ceil_div(L.Nv, num_sms);
   k1.cpt = TILE_M / k2_ppad(d);
   k1.err = err;
   k1.trace = g_trace;
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
-  const int grid1 = ceil_div(d.N, k1.clips_per_cta);
+  const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
   // Token-kernel variants (same results; see profiles/README.md for the measurements):
   //   1  head_sm100_k1.cu, serial tile order -- the default
@@ -1043,7 +1093,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
     return e ? atoi(e) : 1;
   }();
   int variant = g_k1_variant >= 0 ? g_k1_variant : env_variant;
-  if (k1.nsc && (variant == 0 || variant == 3)) variant = 1;   // only the current kernel gathers channels_last input
+  if ((k1.nsc || L.G > 1) && (variant == 0 || variant == 3)) variant = 1;   // channels_last input, voxel-group split: current kernel only
   const bool use_pair = variant == 3 && !k1.f32_in;
   const int phases = variant == 3 ? 1 : variant;
   k1.phases = phases;
@@ -1063,15 +1113,20 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   K2Params k2{};
   k2.feimg = feimg; k2.osum = osum; k2.packed = k1.packed; k2.off_w2 = PL.off_w2; k2.off_b2 = PL.off_b2;
   k2.protos = w.prototypes; k2.last_layer = w.last_layer;
-  k2.logits = logits; k2.sim = sim; k2.dist = dist; k2.feats = feats;
-  k2.labels = push ? push->labels : nullptr;
-  k2.proto_class = push ? push->proto_class : nullptr;
-  k2.global_offset = push ? (long long)push->global_offset : 0;
-  k2.best_key = push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
-  k2.N = d.N; k2.P = d.P; k2.K = d.K;
+  const bool split = L.G > 1;
+  float* featsv = reinterpret_cast<float*>(wsp + L.off_featsv);
+  k2.logits = split ? reinterpret_cast<float*>(wsp + L.off_logv) : logits;
+  k2.sim = split ? reinterpret_cast<float*>(wsp + L.off_simv) : sim;
+  k2.dist = split ? nullptr : dist;
+  k2.feats = split ? featsv : feats;
+  k2.labels = (push && !split) ? push->labels : nullptr;
+  k2.proto_class = (push && !split) ? push->proto_class : nullptr;
+  k2.global_offset = (push && !split) ? (long long)push->global_offset : 0;
+  k2.best_key = (push && !split) ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
+  k2.N = L.Nv; k2.P = d.P; k2.K = d.K;
   k2.cpt = TILE_M / k2_ppad(d);
   k2.PP = k2_ppad(d);
-  k2.ntiles = k2_tiles(d);
+  k2.ntiles = L.tiles2;
   k2.err = err;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;
   {  // programmatic dependent launch: K2's prologue (TMEM, barriers, norms, the resident W2 images) overlaps K1's tail
@@ -1085,13 +1140,22 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   }
   PASN_LAUNCH_CHECK();
   count_launch();
+  if (split) {   // sum the pooled features of the voxel groups, then the fp32 cosine / logits / push stage on real clips
+    float* fe = feats ? feats : reinterpret_cast<float*>(wsp + L.off_fe);
+    const long long tot = (long long)d.N * d.P * DD;
+    sum_groups_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(featsv, fe, d.N, L.G, d.P * DD);
+    PASN_LAUNCH_CHECK();
+    count_launch();
+    const int rc2 = launch_proto_stage(fe, w.prototypes, w.last_layer, d.N, d.P, DD, d.K, logits, sim, dist, push, st);
+    if (rc2) return rc2;
+  }
   return PASN_OK;
 }
 
 // surfaced for tests / debugging: non-zero if a kernel hit its bounded-wait limit (protocol bug) on the last call
 int sm100_last_error(const void* ws, const pasn_dims& d, cudaStream_t st) {
   const char* wsp = reinterpret_cast<const char*>(ws);
-  const int* err = reinterpret_cast<const int*>(wsp + (size_t)k2_tiles(d) * FE_TILE_BYTES + align_up((size_t)d.N * d.P * 4, 256));
+  const int* err = reinterpret_cast<const int*>(wsp + ws_layout(d).off_err);
   int h = 0;
   if (cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;

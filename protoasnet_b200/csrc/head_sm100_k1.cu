@@ -510,11 +510,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const bool valid = t < ntok && !(p.dbg_skip & 2);
         const int clipl = valid ? t / S : 0;
         const int s = valid ? t - clipl * S : 0;
-        const __nv_bfloat16* src = p.feat + ((size_t)(c_begin + clipl) * p.C + kc * 64 + xw * 16) * S + s;
+        // virtual clip -> (real clip, voxel group): rows of the feature map keep the real pitch SR
+        const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
+        const __nv_bfloat16* src = p.feat + ((size_t)rc * p.C + kc * 64 + xw * 16) * p.SR + (size_t)vg * S + s;
         const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * S, valid ? 8u : 0u);
+          cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u);
         cp_async_commit();
         if (g >= XDEPTH - 1) {
           cp_async_wait<XDEPTH - 1>();
@@ -538,9 +540,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const bool valid = t < ntok;
         const int clipl = valid ? t / S : 0;
         const int s = valid ? t - clipl * S : 0;
-        const float* src = p.feat32 + ((size_t)(c_begin + clipl) * p.C + kc * 64 + xw * 16 + 8 * h) * S + s;
+        const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
+        const float* src = p.feat32 + ((size_t)rc * p.C + kc * 64 + xw * 16 + 8 * h) * p.SR + (size_t)vg * S + s;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = valid ? ldg_nc_na_v4f(src + (size_t)j * S) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; ++j) q[j] = valid ? ldg_nc_na_v4f(src + (size_t)j * p.SR) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       auto store32 = [&](uint32_t u, const float4* q) -> bool {
         const uint32_t g = u >> 1, h = u & 1;
@@ -582,18 +585,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           const int t = tile * TILE_M + tok;
           if (t < ntok) {
             const int clipl = t / S, s = t - clipl * S, slot = clipl - first_clip;
-            const size_t o0 = ((size_t)(c_begin + clipl) * p.P) * S + s;
+            const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
+            const size_t o0 = ((size_t)rc * p.P) * p.SR + (size_t)vg * S + s;
             const unsigned char* src = os + off_mnmajor_nosw(slot * PP, tok, NPOOL);
             if (!p.f32_in) {
               __nv_bfloat16* orow = p.occ + o0;
 #pragma unroll 8
               for (int pp = 0; pp < p.P; ++pp)
-                orow[(size_t)pp * S] = *reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2);
+                orow[(size_t)pp * p.SR] = *reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2);
             } else {
               float* orow = p.occ32 + o0;
 #pragma unroll 8
               for (int pp = 0; pp < p.P; ++pp)
-                orow[(size_t)pp * S] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2));
+                orow[(size_t)pp * p.SR] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(src + (pp >> 3) * 128 + (pp & 7) * 2));
             }
           }
         }

@@ -42,6 +42,10 @@ struct K1Params {
   uint8_t* feimg;              // K2 operand images, FE_TILE_BYTES per K2 tile
   float* osum;                 // [N][P]
   int N, C, P, S, nkc, clips_per_cta, cpt;  // cpt = clips per K2 tile = 128 / PP
+  // small batches: every clip is cut into G voxel groups of S voxels that are processed as G independent "clips"
+  // (pooling is linear in the voxels; the partial sums are added after K2).  N and S above are the virtual counts,
+  // SR the real voxel count per clip (= row pitch of the feature map and of the occurrence map).  G = 1: no split.
+  int G, SR;
   int* err;
   long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
   int phases;                  // two-phase kernel: 2 = G / A phases overlapped with the previous chain, 1 = serial order

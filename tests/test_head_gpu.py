@@ -345,3 +345,25 @@ def test_forward_is_cuda_graph_capturable():
             torch.cuda.synchronize()
             el, es, eo = m(x)
             assert torch.equal(logits, el) and torch.equal(sim, es) and torch.equal(occ, eo)
+
+
+def test_small_batch_voxel_group_split_matches_unsplit():
+    """Batches that cannot fill the SMs (cfg 1: 8 clips of 1568 voxels) are processed as G voxel groups per clip whose
+    pooled features are summed after K2.  Same results as the unsplit run (PASN_NO_SPLIT is read once per process, so
+    the unsplit reference here is the generic fp32-math path on the same bf16 inputs) and the fixed-size outputs agree
+    with a larger batch that is not split."""
+    dims = synth.CONFIGS["cfg1_video_yml"]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
+    mg = build_model(dims, sd, path=_lib.PASN_PATH_GENERIC)
+    x = torch.from_numpy(synth.make_features(dims, 80, seed=3, bf16_round=True)).cuda().bfloat16()
+    big = _run_all(m, x)                                  # 80 clips: no split
+    for n in (1, 5, 8):
+        small = _run_all(m, x[:n])                        # split into voxel groups
+        ref = _run_all(mg, x[:n])
+        assert_close(small["similarity"], ref["similarity"].cpu().numpy(), BF16_RTOL, f"similarity n={n}")
+        assert_close(small["logits"], ref["logits"].cpu().numpy(), BF16_RTOL, f"logits n={n}")
+        assert torch.equal(small["distance"], 1 - small["similarity"])
+        assert torch.equal(small["occurrence_map"], big["occurrence_map"][:n])      # per-voxel results do not depend on the split
+        assert_close(small["similarity"], big["similarity"][:n].cpu().numpy(), 1e-4, f"split vs unsplit n={n}")
+        assert_close(small["features_extracted"], big["features_extracted"][:n].cpu().numpy(), 1e-4, f"features n={n}")
