@@ -826,6 +826,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         for (int rep = 0; rep < 2; ++rep) {
           const bool flush = rep == 0 ? boundary : ends;
           if (!flush) continue;
+          if (p.dbg_skip & 8) {   // timing experiment: no hi/lo split, no stores (results garbage)
+            if (rep == 0) {
+#pragma unroll
+              for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < PP; ++j) facc[j] = 0.f;
+            }
+            continue;
+          }
           const int clip = c_begin + (rep == 0 ? first_clip : last_clip);
           // K2's A operand is MN-major (row = (clip,p) contiguous, k = d), so this thread's PP values for its d are
           // PP/8 16-byte chunks per image: rows [rowb, rowb+PP) of k-chunk image d/64, hi at +0 and lo at +64 KB

@@ -49,7 +49,8 @@ struct K1Params {
   int* err;
   long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
   int phases;                  // two-phase kernel: 2 = G / A phases overlapped with the previous chain, 1 = serial order
-  int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X
+  int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X,
+                               // bit3 = do not flush finished clips (head_sm100_k1.cu only)
 };
 
 struct Ctx {
