@@ -353,7 +353,7 @@ def main():
                 "ms_runs_rank0": [round(t, 3) for t in times],
                 "clips_per_sec": n_total / (push_ms * 1e-3), "scaling": "strong",
                 "tensor_frac_of_sustained": f_push / (push_ms * 1e-3) / 1e12 / (world * peaks["bf16_tflops_sustained"]),
-                "winners_sample": idx_ref[:8].tolist(), "collectives_per_push": 2 if world > 1 else 0}
+                "winners_sample": idx_ref[:8].tolist(), "collectives_per_push": 1 if world > 1 else 0}
         model.prototype_vectors.data.copy_(proto0)
         del feats
 

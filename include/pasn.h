@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PASN_ABI_VERSION 1
+#define PASN_ABI_VERSION 2
 
 typedef enum {
   PASN_OK = 0,
@@ -88,15 +88,20 @@ typedef struct {
 } pasn_weights;
 
 /* optional push arguments of pasn_head_forward: fuse the class-restricted running argmin of
- * src/utils/push_abs_revision.py:288-307 into the similarity kernel. */
+ * src/utils/push_abs_revision.py:288-307 into the similarity kernel, and keep the winner's pooled features in the same
+ * pass, as the reference does (:299-302 stashes protoL_input[a, j] from the very forward pass that produced the minimum --
+ * the train_push loader draws a random window per __getitem__, src/data/as_dataloader.py:246-255, so a clip cannot be
+ * re-fetched later). */
 typedef struct {
   const int64_t* labels;      /* [N] ground-truth class of each clip (data_sample["target_AS"])        */
   const int32_t* proto_class; /* [P] class a prototype is restricted to, or -1 for unrestricted        */
                               /*     (abstention prototypes, push_abs_revision.py:231-237)             */
   int64_t global_offset;      /* global index of clip 0 of this call in the unshuffled training set    */
   uint64_t* best_key;         /* [P] in/out running minimum of (orderable(dist) << 32 | global index), stored    */
-                              /*     with the top bit flipped: signed int64 order == key order, so one            */
-                              /*     all-reduce(MIN, int64) merges ranks; INT64_MAX = no candidate yet            */
+                              /*     with the top bit flipped: signed int64 order == key order, so ranks merge    */
+                              /*     by a plain signed minimum; INT64_MAX = no candidate yet                      */
+  float* best_vec;            /* [P][D] in/out or NULL: features_extracted[n*, p, :] of the clip n* that holds    */
+                              /*     best_key[p]; rows of prototypes whose best clip is not in this call are kept */
 } pasn_push_args;
 
 int pasn_abi_version(void);
@@ -164,15 +169,19 @@ int pasn_similarity_stats(const float* similarity, const int64_t* labels, int32_
 int pasn_occurrence_lnorm(const void* occ, int32_t dtype, int64_t rows, int32_t S, int32_t p, double* sum, float* row_norm,
                           void* stream);
 
-/* push bookkeeping (src/utils/push_abs_revision.py:242, :299-300, :342-346) */
+/* push bookkeeping (src/utils/push_abs_revision.py:242, :299-300, :342-346).
+ * A push record is one contiguous buffer  [ best_key: P x u64 | best_vec: P x D x f32 ]  (pasn_push_record_bytes), so that
+ * the merge across ranks is ONE all-gather of the records followed by pasn_push_reduce. */
+size_t pasn_push_record_bytes(int32_t P, int32_t D);
 int pasn_push_init(uint64_t* best_key, int32_t P, void* stream);          /* best_key[:] = +inf / no index */
 int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* index[p] = winner or -1       */
                      float* distance, void* stream);                      /* distance[p] fp32 (inf if none)*/
-/* decode + ownership of range [lo,hi): index, distance, clamped local index (index - lo), own flag, valid flag */
-int pasn_push_select(const uint64_t* best_key, int32_t P, int64_t lo, int64_t hi, int64_t* index, float* distance,
-                     int64_t* local_index, int32_t* own, int32_t* valid, void* stream);
-/* vec[p,:] = own[p] ? feats[p,p,:] : 0, feats = features_extracted [P,P,D] of the P re-fetched winner clips */
-int pasn_push_collect(const float* feats, const int32_t* own, float* vec, int32_t P, int32_t D, void* stream);
+/* gathered = R records back to back (R = 1: this rank's own record).  Per prototype the record with the smallest key
+ * wins (lowest distance, ties to the lowest global index):
+ *   index[p] / distance[p] / valid[p]   decoded winner (index -1, distance +inf, valid 0 when no rank had a candidate)
+ *   vec[p,:]                            its best_vec row (untouched when !valid)                                  */
+int pasn_push_reduce(const void* gathered, int32_t R, int32_t P, int32_t D, int64_t* index, float* distance, int32_t* valid,
+                     float* vec, void* stream);
 /* prototype_vectors[p,:] = vec[p,:] where valid[p] != 0 (else unchanged) */
 int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_t* valid, int32_t P, int32_t D,
                                void* stream);
@@ -187,11 +196,12 @@ float pasn_debug_last_main_kernel_ms(void);
 /* synchronises `stream` and returns the bounded-wait error code the fused tcgen05 kernels left in `workspace`
  * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid) */
 int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream);
-/* device buffer of 3*16*16 int64 that CTA 0 of the fused kernel fills with clock64() stamps per tile phase (NULL = off) */
+/* device buffer of 1024 int64: [0,768) clock64() stamps of CTA 0 of the token kernel per tile phase, [768,1024) globaltimer
+ * stamps of the token kernel start/end and of CTA 0 of the prototype kernel (tools/trace_k1.py, trace_k2.py; NULL = off) */
 int pasn_debug_set_trace(void* device_buffer);
-/* which implementation of the fused token kernel the next calls use (all produce the same results; kept for A/B timing
- * and regression tests): 1 = current kernel, serial tile order (default); 2 = same kernel, two-phase order;
- * 0 = first-generation kernel; 3 = CTA-pair (cta_group::2) variant; -1 = back to the default / PASN_K1_PHASES */
+/* tile order of the fused token kernel for the next calls (same results; kept for A/B timing and regression tests):
+ * 1 = serial (default), 2 = two-phase (layer-1 phases overlapped with the previous tile's chain);
+ * anything else = back to the default / PASN_K1_PHASES */
 int pasn_debug_set_k1_variant(int variant);
 
 #ifdef __cplusplus

@@ -96,6 +96,20 @@ def push_forward_torch(x: torch.Tensor, sd: Dict[str, torch.Tensor]):
     return feats, 1 - sim, occ, logits
 
 
+def push_forward_torch_pchunk(x: torch.Tensor, sd: Dict[str, torch.Tensor], p_chunk: int = 16):
+    """push_forward_torch for shapes whose broadcast product does not fit in memory (BASELINE config 5: P=4096, D=512,
+    S=3136 -> 26 GB per clip).  Same ops as the reference (Video_XProtoNet.py:111-130); the product
+    ``occurrence_map * feature_map`` (:119) is materialised and reduced for ``p_chunk`` prototypes at a time, which does
+    not change any individual sum (each (n,p,d) entry still reduces T, then H, then W of its own row)."""
+    fmap = add_on_torch(x, sd)
+    occ = occurrence_map_torch(x, sd)
+    P = occ.shape[1]
+    feats = torch.cat([pooled_features_torch(occ[:, i:i + p_chunk], fmap) for i in range(0, P, p_chunk)], dim=1)
+    sim = similarity_torch(feats, sd["prototype_vectors"])
+    logits = F.linear(sim, sd["last_layer.weight"])
+    return feats, 1 - sim, occ, logits
+
+
 def to_torch_sd(sd_np: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()}
 

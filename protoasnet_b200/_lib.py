@@ -21,7 +21,7 @@ PASN_PATH_AUTO, PASN_PATH_GENERIC, PASN_PATH_TCGEN05 = 0, 1, 2
 SYMBOLS = [
     "pasn_abi_version", "pasn_strerror", "pasn_tcgen05_supported", "pasn_head_workspace_bytes",
     "pasn_packed_weights_bytes", "pasn_pack_weights", "pasn_head_forward", "pasn_occurrence_only",
-    "pasn_push_init", "pasn_push_decode", "pasn_push_select", "pasn_push_collect", "pasn_push_write_prototypes",
+    "pasn_push_record_bytes", "pasn_push_init", "pasn_push_decode", "pasn_push_reduce", "pasn_push_write_prototypes",
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
     "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant",
     "pasn_head_backward_workspace_bytes", "pasn_head_backward", "pasn_similarity_stats", "pasn_occurrence_lnorm",
@@ -44,7 +44,7 @@ class PasnGrads(C.Structure):
 
 class PasnPushArgs(C.Structure):
     _fields_ = [("labels", C.c_void_p), ("proto_class", C.c_void_p), ("global_offset", C.c_int64),
-                ("best_key", C.c_void_p)]
+                ("best_key", C.c_void_p), ("best_vec", C.c_void_p)]
 
 
 class PasnError(RuntimeError):
@@ -85,10 +85,10 @@ def load() -> C.CDLL:
     lib.pasn_push_init.argtypes = [vp, i32, vp]
     lib.pasn_push_decode.restype = C.c_int
     lib.pasn_push_decode.argtypes = [vp, i32, vp, vp, vp]
-    lib.pasn_push_select.restype = C.c_int
-    lib.pasn_push_select.argtypes = [vp, i32, i64, i64, vp, vp, vp, vp, vp, vp]
-    lib.pasn_push_collect.restype = C.c_int
-    lib.pasn_push_collect.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.pasn_push_record_bytes.restype = sz
+    lib.pasn_push_record_bytes.argtypes = [i32, i32]
+    lib.pasn_push_reduce.restype = C.c_int
+    lib.pasn_push_reduce.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.pasn_push_write_prototypes.restype = C.c_int
     lib.pasn_push_write_prototypes.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.pasn_debug_launch_count.restype = C.c_ulonglong
@@ -111,7 +111,7 @@ def load() -> C.CDLL:
     lib.pasn_debug_set_k1_variant.argtypes = [C.c_int]
     lib.pasn_debug_sm100_error.restype = C.c_int
     lib.pasn_debug_sm100_error.argtypes = [vp, C.POINTER(PasnDims), vp]
-    if lib.pasn_abi_version() != 1:
+    if lib.pasn_abi_version() != 2:
         raise PasnError("libpasn_b200.so ABI version mismatch")
     _lib = lib
     return lib

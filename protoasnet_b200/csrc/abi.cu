@@ -134,7 +134,7 @@ extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const 
   if (!dims_ok(dims) || !w || !logits || !similarity) return PASN_ERR_INVALID;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
-  if (push && (!push->labels || !push->proto_class || !push->best_key)) return PASN_ERR_INVALID;
+  if (push && (!push->labels || !push->proto_class || !push->best_key)) return PASN_ERR_INVALID;   // best_vec is optional
   if (push && (push->global_offset < 0 || push->global_offset + dims->N > 0xFFFFFFFFll)) return PASN_ERR_INVALID;
   int err;
   if (use_tcgen05(*dims, packed, &err))

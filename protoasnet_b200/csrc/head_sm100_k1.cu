@@ -129,6 +129,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   __syncthreads();
   tc_fence_after();
   griddep_launch_dependents();   // K2 may start launching (its CTAs only fit on an SM once one of ours has exited)
+  if constexpr (TRACE) {
+    if (tid == 0 && p.trace != nullptr && blockIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.trace[768 + 0] = t;
+    }
+  }
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t x_base = smem_u32(smem + SM_X), w_base = smem_u32(smem + SM_W), os_base = smem_u32(smem + SM_OS);
   const int nkc = p.nkc;
@@ -871,6 +878,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, 512);
+  if constexpr (TRACE) {   // wall-clock end of CTA 0 (ns), next to K2's stamps (tools/trace_k2.py)
+    if (tid == 0 && p.trace != nullptr && blockIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.trace[768 + 1] = t;
+    }
+  }
 }
 
 template <int PP, bool TRACE>

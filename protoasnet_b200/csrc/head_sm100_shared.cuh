@@ -105,7 +105,5 @@ __device__ __forceinline__ void bias_relu_pack(const uint32_t (&r)[32], const fl
 
 // two-phase token kernel (head_sm100_k1.cu)
 int launch_k1_two_phase(const k1::K1Params& k1p, int ppad, int grid, cudaStream_t st);
-// pair variant (head_sm100_pair.cu)
-int launch_k1_pair(const k1::K1Params& k1p, int ppad, cudaStream_t st);
 
 }  // namespace pasn

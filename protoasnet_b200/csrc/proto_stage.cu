@@ -79,6 +79,19 @@ __global__ void __launch_bounds__(PS_THREADS) proto_stage_kernel(
       if (s_key[p] != PASN_KEY_NONE) key_atomic_min_global(&best_key[p], s_key[p]);
 }
 
+// best_vec[p,:] = feats[n*,p,:] where n* = clip of this call that holds best_key[p] (keys carry the global clip index);
+// prototypes whose best clip lies outside [offset, offset+N) keep their row.  One block per prototype.
+__global__ void push_capture_dense_kernel(const unsigned long long* __restrict__ best_key, int P, int D, long long offset,
+                                          int N, const float* __restrict__ feats, float* __restrict__ best_vec) {
+  const int p = blockIdx.x;
+  const unsigned long long key = best_key[p] ^ PASN_KEY_SIGN;
+  if (key == PASN_KEY_NONE) return;
+  const long long idx = (long long)(key & 0xFFFFFFFFull);
+  if (idx < offset || idx >= offset + N) return;
+  const float* src = feats + ((size_t)(idx - offset) * P + p) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) best_vec[(size_t)p * D + d] = src[d];
+}
+
 int launch_proto_stage(const float* feats, const float* protos, const float* last_layer, int N, int P, int D, int K,
                        float* logits, float* sim, float* dist, const pasn_push_args* push, cudaStream_t st) {
   if (N <= 0) return PASN_OK;
@@ -94,6 +107,12 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
       push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr);
   PASN_LAUNCH_CHECK();
   count_launch();
+  if (push && push->best_vec) {   // winner capture in the same pass (push_abs_revision.py:299-302)
+    push_capture_dense_kernel<<<P, 128, 0, st>>>(reinterpret_cast<const unsigned long long*>(push->best_key), P, D,
+                                                 (long long)push->global_offset, N, feats, push->best_vec);
+    PASN_LAUNCH_CHECK();
+    count_launch();
+  }
   return PASN_OK;
 }
 
@@ -104,10 +123,8 @@ __global__ void push_init_kernel(unsigned long long* k, int P) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P) k[i] = PASN_KEY_NONE ^ PASN_KEY_SIGN;   // INT64_MAX in the signed-order global format
 }
-// decode + ownership in one launch: index / distance of the winner, whether this rank's range [lo, hi) owns it, and the
-// (clamped) local index to re-fetch it from
-__global__ void push_select_kernel(const unsigned long long* k, int P, long long lo, long long hi, int64_t* index,
-                                   float* distance, int64_t* local_index, int32_t* own, int32_t* valid) {
+// decode: index / distance of the winner per prototype
+__global__ void push_decode_kernel(const unsigned long long* k, int P, int64_t* index, float* distance) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const unsigned long long key = k[i] ^ PASN_KEY_SIGN;
@@ -119,19 +136,29 @@ __global__ void push_select_kernel(const unsigned long long* k, int P, long long
   }
   index[i] = idx;
   if (distance) distance[i] = d;
-  if (valid) valid[i] = idx >= 0;
-  if (own) own[i] = idx >= lo && idx < hi;
-  if (local_index) {
-    long long l = idx < lo ? lo : (idx >= hi ? hi - 1 : idx);
-    local_index[i] = hi > lo ? l - lo : 0;
-  }
 }
-// vec[p,:] = own[p] ? feats[p,p,:] : 0   (feats = push_forward output over the P re-fetched winner clips)
-__global__ void push_collect_kernel(const float* feats, const int32_t* own, float* vec, int P, int D) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)P * D) return;
-  const int p = (int)(i / D), d = (int)(i - (long long)p * D);
-  vec[i] = own[p] ? feats[((size_t)p * P + p) * D + d] : 0.f;
+// merge of R push records [keys P x u64 | vecs P x D x f32]: per prototype (one block) the smallest signed key wins
+__global__ void push_reduce_kernel(const unsigned char* __restrict__ gathered, size_t rec_bytes, int R, int P, int D,
+                                   int64_t* __restrict__ index, float* __restrict__ distance, int32_t* __restrict__ valid,
+                                   float* __restrict__ vec) {
+  const int p = blockIdx.x;
+  long long best = 0x7FFFFFFFFFFFFFFFll;
+  int rb = 0;
+  for (int r = 0; r < R; ++r) {
+    const long long k = reinterpret_cast<const long long*>(gathered + (size_t)r * rec_bytes)[p];
+    if (k < best) { best = k; rb = r; }
+  }
+  const unsigned long long key = (unsigned long long)best ^ PASN_KEY_SIGN;
+  const bool ok = key != PASN_KEY_NONE;
+  if (threadIdx.x == 0) {
+    index[p] = ok ? (long long)(key & 0xFFFFFFFFull) : -1;
+    if (distance) distance[p] = ok ? f32_from_orderable((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
+    if (valid) valid[p] = ok ? 1 : 0;
+  }
+  if (ok && vec) {
+    const float* src = reinterpret_cast<const float*>(gathered + (size_t)rb * rec_bytes + (size_t)P * 8) + (size_t)p * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) vec[(size_t)p * D + d] = src[d];
+  }
 }
 __global__ void push_write_kernel(float* protos, const float* vec, const int32_t* valid, int P, int D) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,27 +177,23 @@ extern "C" int pasn_push_init(uint64_t* best_key, int32_t P, void* stream) {
   count_launch();
   return PASN_OK;
 }
+extern "C" size_t pasn_push_record_bytes(int32_t P, int32_t D) {
+  return (P > 0 && D > 0) ? (size_t)P * 8 + (size_t)P * D * 4 : 0;
+}
 extern "C" int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, float* distance, void* stream) {
   if (!best_key || !index || P <= 0) return PASN_ERR_INVALID;
-  push_select_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const unsigned long long*>(best_key), P, 0, 0, index, distance, nullptr, nullptr, nullptr);
+  push_decode_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(best_key), P, index, distance);
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;
 }
-extern "C" int pasn_push_select(const uint64_t* best_key, int32_t P, int64_t lo, int64_t hi, int64_t* index,
-                                float* distance, int64_t* local_index, int32_t* own, int32_t* valid, void* stream) {
-  if (!best_key || !index || P <= 0 || hi < lo) return PASN_ERR_INVALID;
-  push_select_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const unsigned long long*>(best_key), P, lo, hi, index, distance, local_index, own, valid);
-  PASN_LAUNCH_CHECK();
-  count_launch();
-  return PASN_OK;
-}
-extern "C" int pasn_push_collect(const float* feats, const int32_t* own, float* vec, int32_t P, int32_t D, void* stream) {
-  if (!feats || !own || !vec || P <= 0 || D <= 0) return PASN_ERR_INVALID;
-  long long n = (long long)P * D;
-  push_collect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(feats, own, vec, P, D);
+extern "C" int pasn_push_reduce(const void* gathered, int32_t R, int32_t P, int32_t D, int64_t* index, float* distance,
+                                int32_t* valid, float* vec, void* stream) {
+  if (!gathered || !index || R <= 0 || P <= 0 || D <= 0) return PASN_ERR_INVALID;
+  if (((uintptr_t)gathered & 7) != 0) return PASN_ERR_ALIGN;
+  push_reduce_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned char*>(gathered),
+                                                          pasn_push_record_bytes(P, D), R, P, D, index, distance, valid, vec);
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;

@@ -126,7 +126,7 @@ class _HeadRuntime:
                 pa = None
                 if push is not None:
                     pa = PasnPushArgs(push["labels"].data_ptr(), push["proto_class"].data_ptr(),
-                                      int(push["global_offset"]), push["best_key"].data_ptr())
+                                      int(push["global_offset"]), push["best_key"].data_ptr(), _ptr(push.get("best_vec")))
                 st = lib.pasn_head_forward(x.data_ptr(), C.byref(w), _ptr(packed), C.byref(dims), logits.data_ptr(),
                                            sim.data_ptr(), _ptr(occ), _ptr(feats), _ptr(dist),
                                            C.byref(pa) if pa is not None else None, ws.data_ptr(), ws.numel(), stream)
@@ -423,12 +423,16 @@ class PrototypeHeadMixin:
         return r["features_extracted"], r["distance"], r["occurrence_map"], r["logits"]
 
     # ---- B200 extension used by push (no per-batch D2H, no occurrence-map store) ----
-    def push_scan(self, x, labels, proto_class, global_offset, best_key, backbone=True):
-        """Fused similarity + class-restricted running argmin over one batch; updates ``best_key`` in place."""
+    def push_scan(self, x, labels, proto_class, global_offset, best_key, backbone=True, best_vec=None):
+        """Fused similarity + class-restricted running argmin over one batch; updates ``best_key`` (and, when given,
+        the winners' ``features_extracted`` rows ``best_vec`` [P,D] fp32) in place."""
         if backbone:
             x = self.cnn_backbone(x)
+        if best_vec is not None and (best_vec.dtype != torch.float32 or not best_vec.is_contiguous()):
+            raise _lib.PasnError("best_vec must be a contiguous fp32 [P,D] tensor")
         return self._rt.run(x, want_occ=False, push=dict(labels=labels, proto_class=proto_class,
-                                                           global_offset=global_offset, best_key=best_key))
+                                                           global_offset=global_offset, best_key=best_key,
+                                                           best_vec=best_vec))
 
     def _rt_push_forward_features(self, feats_in):
         """push_forward on an already-computed backbone feature map (winner re-fetch in push pass 2)."""

@@ -3,16 +3,18 @@
 Mirrors ``push_prototypes`` of the reference (src/utils/push_abs_revision.py:181-348) and the agent wrapper
 ``XProtoNet_Base.push`` (src/agents/XProtoNet_Base.py:149-167), re-designed for B200:
 
-  pass 1  every rank walks its contiguous shard of the unshuffled ``train_push`` set; per batch ONE fused launch
-          computes the head and folds the class-restricted running argmin into packed keys
-          ``orderable(fp32 dist) << 32 | global index`` kept on device (no per-batch D2H of features, distances,
-          occurrence maps or input clips as at push_abs_revision.py:278-285).
-  merge   one NCCL all-reduce(MIN) over the P packed keys (ties -> lowest global index).
-  pass 2  the owner rank of each winner re-runs ``push_forward`` on just those <= P clips to obtain the winning
-          ``features_extracted`` rows and the side data the reference pickles (occurrence map, logits, label,
-          filename, input clip; push_abs_revision.py:301-325); one all-reduce(SUM) of the [P,D] fp32 winner rows
-          (non-owners contribute exact zeros), then every rank overwrites ``prototype_vectors`` identically
-          (push_abs_revision.py:342-346).
+  scan    every rank walks its contiguous shard of the unshuffled ``train_push`` set; per batch ONE fused launch pair
+          computes the head, folds the class-restricted running argmin into packed keys
+          ``orderable(fp32 dist) << 32 | global index`` AND keeps the winner's ``features_extracted`` row -- both in one
+          device record ``[keys P x u64 | vectors P x D x f32]``.  The winner is captured in the pass that saw it, as the
+          reference does (push_abs_revision.py:299-307): its push loader draws a random window per ``__getitem__``
+          (src/data/as_dataloader.py:246-255), so a clip cannot be fetched a second time.  No per-batch D2H of features,
+          distances, occurrence maps or input clips (push_abs_revision.py:278-285).
+  merge   ONE collective: all-gather of the records (41 KB per rank at P=40, D=256); every rank then picks, per
+          prototype, the record with the smallest key (lowest distance, ties -> lowest global index) and overwrites
+          ``prototype_vectors`` identically (push_abs_revision.py:342-346).
+  side    with a Dataset loader the data the reference pickles (occurrence map, logits, label, filename, input clip;
+          push_abs_revision.py:301-325) is taken from the batch that improved a prototype, while it is still in memory.
 
 Defined behaviour where the reference crashes: a class-specific prototype whose class never occurs keeps its old
 vector and reports index -1 (SURVEY.md section 7 'Empty class').  Rendering of prototype images / mp4s
@@ -24,7 +26,7 @@ from __future__ import annotations
 import os
 import pickle
 import time
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -49,23 +51,43 @@ def proto_class_restriction(model, class_specific: bool = True, abstain_class: b
 
 def new_best_key(P: int, device) -> torch.Tensor:
     key = torch.empty(P, dtype=torch.int64, device=device)  # storage for uint64 keys
-    lib = _lib.load()
-    with torch.cuda.device(device):
-        _lib.check(lib.pasn_push_init(key.data_ptr(), P, torch.cuda.current_stream(device).cuda_stream), "pasn_push_init")
+    _init_key(key)
     return key
 
 
+def _init_key(key: torch.Tensor) -> None:
+    lib = _lib.load()
+    dev = key.device
+    with torch.cuda.device(dev):
+        _lib.check(lib.pasn_push_init(key.data_ptr(), key.numel(), torch.cuda.current_stream(dev).cuda_stream), "pasn_push_init")
+
+
+class PushRecord:
+    """One rank's running push state in ONE device buffer ``[keys: P x u64 | vectors: P x D x f32]`` (include/pasn.h,
+    ``pasn_push_record_bytes``): ``key`` and ``vec`` are views, ``buf`` is what the all-gather moves."""
+
+    def __init__(self, P: int, D: int, device):
+        self.P, self.D = int(P), int(D)
+        self.buf = torch.zeros(self.P * 8 + self.P * self.D * 4, dtype=torch.uint8, device=device)
+        self.key = self.buf[: self.P * 8].view(torch.int64)
+        self.vec = self.buf[self.P * 8:].view(torch.float32).view(self.P, self.D)
+        if self.buf.is_cuda:
+            _init_key(self.key)
+        else:   # host-side bookkeeping only (gloo tests of the merge logic)
+            self.key.fill_(_KEY_NONE)
+
+
+_KEY_NONE = (1 << 63) - 1   # INT64_MAX: no candidate
+
+
 def merge_keys(best_key: torch.Tensor, group=None) -> torch.Tensor:
-    """All-reduce(MIN) of the packed keys.  They are stored with the top bit flipped (include/pasn.h), so the signed
-    int64 order NCCL / gloo reduce with is the key order: lowest distance first, ties to the lowest global index."""
+    """All-reduce(MIN) of packed keys alone (kept for callers that only need indices).  Keys are stored with the top bit
+    flipped (include/pasn.h), so the signed int64 order NCCL / gloo reduce with is the key order."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(best_key, op=dist.ReduceOp.MIN, group=group)
     return best_key
-
-
-_KEY_NONE = (1 << 63) - 1   # INT64_MAX: no candidate
 
 
 def decode_keys(best_key: torch.Tensor):
@@ -96,64 +118,58 @@ def _world(group=None):
     return 0, 1
 
 
-def finish_push(model, best_key, fetch_features, lo: int, hi: int, replace_prototypes=True, group=None, dense=False):
-    """Merge keys across ranks, gather winner rows from their owners, overwrite prototypes.
-
-    ``fetch_features(global_indices: LongTensor on device) -> backbone feature maps`` for indices in [lo, hi).
-    ``dense=True`` (features resident on the GPU): no host synchronisation at all -- every rank re-runs ``push_forward``
-    on exactly P clips (its winners, or a clamped in-range clip where it is not the owner) and masks by ownership.
-    ``dense=False`` (clips come from a Dataset): only the distinct local winners are fetched.
-    Returns dict(index, distance, features (P,D), side) -- ``side`` carries the winners' occurrence maps / logits.
-    """
+def gather_records(rec: PushRecord, group=None) -> Tuple[torch.Tensor, int]:
+    """The one collective of a push: all-gather of the ranks' records -> (R records back to back, R)."""
     import torch.distributed as dist
 
-    lib = _lib.load()
-    dev = best_key.device
-    P, D = model.num_prototypes, model.prototype_shape[1]
-    merge_keys(best_key, group)
-    side = {}
-    if dense:
-        # one launch decodes the keys and derives ownership / clamped local indices; one launch collects the rows
-        idx = torch.empty(P, dtype=torch.int64, device=dev)
-        dmin = torch.empty(P, dtype=torch.float32, device=dev)
-        local = torch.empty(P, dtype=torch.int64, device=dev)
-        own = torch.empty(P, dtype=torch.int32, device=dev)
-        valid = torch.empty(P, dtype=torch.int32, device=dev)
-        vec = torch.empty((P, D), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            st = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.pasn_push_select(best_key.data_ptr(), P, lo, hi, idx.data_ptr(), dmin.data_ptr(),
-                                            local.data_ptr(), own.data_ptr(), valid.data_ptr(), st), "pasn_push_select")
-            if hi > lo:
-                feats, dist_w, occ, logits = model._rt_push_forward_features(fetch_features(local + lo))
-                _lib.check(lib.pasn_push_collect(feats.data_ptr(), own.data_ptr(), vec.data_ptr(), P, D, st),
-                           "pasn_push_collect")
-                side = {"owned": own, "occurrence_maps": occ, "logits": logits, "distance": dist_w}  # row p <-> prototype p
-            else:
-                vec.zero_()
+    _, world = _world(group)
+    if world == 1:
+        return rec.buf, 1
+    out = torch.empty(world * rec.buf.numel(), dtype=torch.uint8, device=rec.buf.device)
+    if rec.buf.is_cuda:
+        dist.all_gather_into_tensor(out, rec.buf, group=group)
     else:
-        idx, dmin = decode_keys(best_key)
-        mine = (idx >= lo) & (idx < hi)
+        dist.all_gather(list(out.view(world, -1).unbind(0)), rec.buf, group=group)
+    return out, world
+
+
+def reduce_records(gathered: torch.Tensor, R: int, P: int, D: int):
+    """Per prototype the record with the smallest key wins -> (index, distance, valid int32, vec [P,D])."""
+    dev = gathered.device
+    if not gathered.is_cuda:   # host-side bookkeeping only (gloo tests of the merge logic)
+        recs = gathered.view(R, -1)
+        keys = torch.stack([recs[r, : P * 8].view(torch.int64) for r in range(R)])
+        vecs = torch.stack([recs[r, P * 8:].view(torch.float32).view(P, D) for r in range(R)])
+        best, who = keys.min(dim=0)
+        idx, d = decode_keys(best)
         valid = (idx >= 0).to(torch.int32)
-        vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
-        if bool(mine.any()):
-            protos = torch.nonzero(mine).flatten()
-            uniq, inv = torch.unique(idx[protos], return_inverse=True)
-            x = fetch_features(uniq)
-            feats, dist_w, occ, logits = model._rt_push_forward_features(x)
-            vec[protos] = feats[inv, protos]
-            side = {"prototypes": protos, "clips": uniq, "inv": inv, "occurrence_maps": occ[inv, protos],
-                    "logits": logits[inv], "distance": dist_w[inv, protos]}
-    rank, world = _world(group)
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        vec = vecs[who, torch.arange(P)] * valid[:, None]
+        return idx, d, valid, vec
+    lib = _lib.load()
+    idx = torch.empty(P, dtype=torch.int64, device=dev)
+    d = torch.empty(P, dtype=torch.float32, device=dev)
+    valid = torch.empty(P, dtype=torch.int32, device=dev)
+    vec = torch.zeros((P, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pasn_push_reduce(gathered.data_ptr(), R, P, D, idx.data_ptr(), d.data_ptr(), valid.data_ptr(),
+                                        vec.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pasn_push_reduce")
+    return idx, d, valid, vec
+
+
+def finish_push(model, rec: PushRecord, replace_prototypes=True, group=None):
+    """One all-gather of the records, per-prototype minimum, prototype overwrite.  No host synchronisation.
+    Returns dict(index, distance, features (P,D), valid)."""
+    lib = _lib.load()
+    gathered, R = gather_records(rec, group)
+    idx, dmin, valid, vec = reduce_records(gathered, R, rec.P, rec.D)
     if replace_prototypes:
         pv = model.prototype_vectors.data
+        dev = pv.device
         with torch.cuda.device(dev):
-            _lib.check(lib.pasn_push_write_prototypes(pv.data_ptr(), vec.data_ptr(), valid.data_ptr(), P, D,
+            _lib.check(lib.pasn_push_write_prototypes(pv.data_ptr(), vec.data_ptr(), valid.data_ptr(), rec.P, rec.D,
                                                       torch.cuda.current_stream(dev).cuda_stream),
                        "pasn_push_write_prototypes")
-    return {"index": idx, "distance": dmin, "features": vec, "side": side}
+    return {"index": idx, "distance": dmin, "features": vec, "valid": valid, "side": {}}
 
 
 def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_offset: int = 0, n_total: Optional[int] = None,
@@ -161,18 +177,14 @@ def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_of
     """Push over backbone feature maps already resident on this rank's GPU (``features`` [n_local,C,*spatial],
     ``labels`` int64 [n_local]); ``global_offset`` = global index of local clip 0.  This is the path bench.py times."""
     dev = features.device
-    P = model.num_prototypes
+    P, D = model.num_prototypes, model.prototype_shape[1]
     pc = proto_class_restriction(model, class_specific, abstain_class).to(dev)
-    key = new_best_key(P, dev)
+    rec = PushRecord(P, D, dev)
     n_local = features.shape[0]
     for i in range(0, n_local, chunk):
-        model.push_scan(features[i:i + chunk], labels[i:i + chunk], pc, global_offset + i, key, backbone=False)
-    lo, hi = global_offset, global_offset + n_local
-
-    def fetch(gidx):
-        return features.index_select(0, gidx - lo)
-
-    return finish_push(model, key, fetch, lo, hi, replace_prototypes, group, dense=True)
+        model.push_scan(features[i:i + chunk], labels[i:i + chunk], pc, global_offset + i, rec.key, backbone=False,
+                        best_vec=rec.vec)
+    return finish_push(model, rec, replace_prototypes, group)
 
 
 def push_prototypes(
@@ -192,8 +204,9 @@ def push_prototypes(
 ):
     """Same signature and effect as the reference's ``push_prototypes`` (push_abs_revision.py:181-196).
 
-    ``dataloader`` yields dicts with ``"cine"`` [B,3,(T),H,W], ``"target_AS"`` [B] and ``"filename"``; it must be
-    unshuffled (src/data/as_dataloader.py:65) and expose ``.dataset`` with ``__getitem__`` for the winner re-fetch.
+    ``dataloader`` yields dicts with ``"cine"`` [B,3,(T),H,W], ``"target_AS"`` [B] and ``"filename"``, unshuffled
+    (src/data/as_dataloader.py:65).  Every clip is seen exactly once: the winners' vectors and side data are captured
+    from the batch that produced them, so a loader whose ``__getitem__`` is random (as the reference's is) is fine.
     Under torch.distributed every rank calls this with the SAME loader; rank r processes the batches whose global
     clip range falls in its shard.
     """
@@ -207,69 +220,71 @@ def push_prototypes(
         os.makedirs(proto_epoch_dir, exist_ok=True)
 
     dev = model.prototype_vectors.device
-    P = model.num_prototypes
+    P, D = model.num_prototypes, model.prototype_shape[1]
     pc = proto_class_restriction(model, class_specific, abstain_class).to(dev)
-    key = new_best_key(P, dev)
+    rec = PushRecord(P, D, dev)
     rank, world = _world(group)
     n_batches = len(dataloader)
     per = -(-n_batches // world)
     b_lo, b_hi = min(rank * per, n_batches), min((rank + 1) * per, n_batches)
 
+    # side data of the current winner of each prototype (push_abs_revision.py:301-307), taken from the batch that
+    # improved it while that batch is still in memory
+    side = {j: None for j in range(P)}
+    want_side = proto_epoch_dir is not None
+    protos = []
     offset = 0
-    lo = hi = None
     with torch.no_grad():
         for bi, data_sample in enumerate(dataloader):
             x = data_sample["cine"]
             B = x.shape[0]
             if b_lo <= bi < b_hi:
-                if lo is None:
-                    lo = offset
                 if preprocess_input_function is not None:
                     x = preprocess_input_function(x)
-                x = x.to(dev, non_blocking=True)
+                xd = x.to(dev, non_blocking=True)
                 y = data_sample["target_AS"].to(dev, non_blocking=True).to(torch.int64)
-                model.push_scan(x, y, pc, offset, key)
-                hi = offset + B
+                fmap = model.cnn_backbone(xd)
+                prev = rec.key.clone() if want_side else None
+                model.push_scan(fmap, y, pc, offset, rec.key, backbone=False, best_vec=rec.vec)
+                if want_side:
+                    changed = torch.nonzero(rec.key != prev).flatten()
+                    if changed.numel():                       # O(P log N) batches in total
+                        idx_now, _ = decode_keys(rec.key)
+                        local = (idx_now[changed] - offset)
+                        uniq, inv = torch.unique(local, return_inverse=True)
+                        _f, _d, occ, logits = model._rt_push_forward_features(fmap.index_select(0, uniq))
+                        occ_rows = occ[inv, changed].float().cpu().numpy()
+                        lg = logits[inv].float().cpu().numpy()
+                        names = data_sample.get("filename", None)
+                        for t, (j, a) in enumerate(zip(changed.tolist(), local.tolist())):
+                            side[j] = {"occurrence_map": occ_rows[t], "logits": lg[t], "image": np.asarray(x[a]),
+                                       "gt": int(data_sample["target_AS"][a]),
+                                       "filename": names[a] if names is not None else str(offset + a)}
             offset += B
-    if lo is None:
-        lo = hi = 0
-
-    dataset = getattr(dataloader, "dataset", None)
-    fetched = {}
-
-    def fetch(gidx):
-        clips = []
-        for g in gidx.tolist():
-            sample = dataset[g]
-            fetched[g] = sample
-            xi = sample["cine"]
-            if preprocess_input_function is not None:
-                xi = preprocess_input_function(xi.unsqueeze(0)).squeeze(0)
-            clips.append(xi)
-        xb = torch.stack(clips).to(dev)
-        with torch.no_grad():
-            return model.cnn_backbone(xb)
 
     with torch.no_grad():
-        res = finish_push(model, key, fetch, lo, hi, replace_prototypes, group)
+        res = finish_push(model, rec, replace_prototypes, group)
 
-    # side data in the reference's pickle schema (push_abs_revision.py:309-325); local winners only under DDP
-    side = res["side"]
-    if proto_epoch_dir is not None and side:
-        protos = side["prototypes"].tolist()
-        clips = side["clips"][side["inv"]].tolist()
-        info = {
-            "prototype_ids": np.asarray(protos),
-            "prototypes_filenames": np.array([fetched[g].get("filename", str(g)) for g in clips]),
-            "prototypes_src_imgs": np.array([np.asarray(fetched[g]["cine"]) for g in clips]),
-            "prototypes_gts": np.array([int(fetched[g]["target_AS"]) for g in clips]),
-            "prototypes_preds": side["logits"].float().cpu().numpy(),
-            "prototypes_occurrence_maps": side["occurrence_maps"].float().cpu().numpy(),
-            "prototypes_similarity_to_src_ROIs": 1 - res["distance"][side["prototypes"]].double().cpu().numpy(),
-        }
-        suffix = "" if world == 1 else f".rank{rank}"
-        with open(os.path.join(proto_epoch_dir, f"prototypes_info{suffix}.pickle"), "wb") as f:
-            pickle.dump(info, f)
+    # side data in the reference's pickle schema (push_abs_revision.py:309-325); under DDP each rank writes the winners
+    # that its own shard produced
+    if want_side:
+        idx_local, _ = decode_keys(rec.key)
+        mine = (idx_local == res["index"]) & (res["index"] >= 0)
+        protos = [j for j in torch.nonzero(mine).flatten().tolist() if side[j] is not None]
+        if protos:
+            info = {
+                "prototype_ids": np.asarray(protos),
+                "prototypes_filenames": np.array([side[j]["filename"] for j in protos]),
+                "prototypes_src_imgs": np.array([side[j]["image"] for j in protos]),
+                "prototypes_gts": np.array([side[j]["gt"] for j in protos]),
+                "prototypes_preds": np.array([side[j]["logits"] for j in protos]),
+                "prototypes_occurrence_maps": np.array([side[j]["occurrence_map"] for j in protos]),
+                "prototypes_similarity_to_src_ROIs": 1 - res["distance"][protos].double().cpu().numpy(),
+            }
+            suffix = "" if world == 1 else f".rank{rank}"
+            with open(os.path.join(proto_epoch_dir, f"prototypes_info{suffix}.pickle"), "wb") as f:
+                pickle.dump(info, f)
+        res["side"] = {j: side[j] for j in protos}
     log("\tpush time: \t{0}".format(time.time() - start))
     return res
 

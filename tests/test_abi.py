@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == sorted(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.pasn_abi_version() == 1
+    assert lib.pasn_abi_version() == 2
     assert lib.pasn_strerror(0) == b"ok"
     assert b"workspace" in lib.pasn_strerror(-2)
 

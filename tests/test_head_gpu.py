@@ -56,6 +56,54 @@ def test_bf16_matches_reference_golden(case):
     # the map itself is stored in bf16 and computed from bf16 hidden activations: entries are judged against the
     # map's scale (|.| of a near-zero pre-activation has no meaningful relative error)
     assert_close(out["occurrence_map"], z["occurrence_map"], 2e-2, "occurrence_map (bf16)", atol_frac=1e-2)
+    # compute_occurence_map (Video_XProtoNet.py:100-109) and push_forward's copy of the map, bf16 output
+    assert out["occ3"].dtype == torch.bfloat16 and out["occ3"].shape == out["occurrence_map"].shape
+    assert_close(out["occ3"], z["occurrence_map"], 2e-2, "compute_occurence_map (bf16)", atol_frac=1e-2)
+    assert_close(out["occ2"], z["occurrence_map"], 2e-2, "push_forward occurrence_map (bf16)", atol_frac=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cfg5_scaled_sweep_matches_oracle(dtype):
+    """BASELINE config 5 (P=4096, D=512, C=512, 16x14x14 feature maps) at N=2 against the CPU oracle (the reference's ops
+    with the broadcast product reduced 16 prototypes at a time -- the full product would need 26 GB per clip)."""
+    dims = synth.CONFIGS["cfg5_scaled"]
+    bf = dtype == torch.bfloat16
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=bf)
+    x = synth.make_features(dims, 2, seed=3, bf16_round=bf)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch_pchunk(torch.from_numpy(x), ho.to_torch_sd(sd), p_chunk=16)
+    m = build_model(dims, sd)
+    out = _run_all(m, torch.from_numpy(x).cuda().to(dtype))
+    tol = BF16_RTOL if bf else FP32_RTOL
+    assert_close(out["logits"], rl.numpy(), tol, "logits")
+    assert_close(out["similarity"], (1 - rd).numpy(), tol, "similarity")
+    assert_close(out["distance"], rd.numpy(), tol, "distance", atol_frac=tol)
+    if bf:
+        assert_close(out["features_extracted"], rf.numpy(), 4e-3, "features_extracted")
+        assert_close(out["occurrence_map"], ro.numpy(), 2e-2, "occurrence_map (bf16)", atol_frac=1e-2)
+        assert_close(out["occ3"], ro.numpy(), 2e-2, "compute_occurence_map (bf16)", atol_frac=1e-2)
+    else:
+        assert_close(out["features_extracted"], rf.numpy(), FP32_RTOL, "features_extracted")
+        assert_close(out["occurrence_map"], ro.numpy(), FP32_RTOL, "occurrence_map")
+        assert_close(out["occ3"], ro.numpy(), FP32_RTOL, "compute_occurence_map")
+    assert torch.equal(out["distance"], 1 - out["similarity"])
+
+
+def test_cfg2_image_bf16_matches_oracle():
+    """BASELINE config 2 (image head, D=512, 7x7) in bf16 at the push-loader batch of 150 (as_dataloader.py:49-50)."""
+    dims = synth.CONFIGS["cfg2_image"]
+    sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
+    x = synth.make_features(dims, 150, seed=5, bf16_round=True)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x), ho.to_torch_sd(sd))
+    m = build_model(dims, sd)
+    out = _run_all(m, torch.from_numpy(x).cuda().bfloat16())
+    assert_close(out["logits"], rl.numpy(), BF16_RTOL, "logits")
+    assert_close(out["similarity"], (1 - rd).numpy(), BF16_RTOL, "similarity")
+    assert_close(out["features_extracted"], rf.numpy(), 4e-3, "features_extracted")
+    assert_close(out["occurrence_map"], ro.numpy(), 2e-2, "occurrence_map (bf16)", atol_frac=1e-2)
+    assert_close(out["occ3"], ro.numpy(), 2e-2, "compute_occurence_map (bf16)", atol_frac=1e-2)
 
 
 SHAPES = [
@@ -244,9 +292,9 @@ VARIANT_SHAPES = [(512, 40, 4, (4, 7, 7), 37), (256, 24, 4, (8, 14, 14), 2), (12
 
 @pytest.mark.parametrize("shape", VARIANT_SHAPES, ids=[str(s) for s in VARIANT_SHAPES])
 def test_token_kernel_variants_agree(shape):
-    """The kept implementations of the fused token kernel (current serial / two-phase order, first generation, CTA
-    pair) are interchangeable: same TMEM-accumulated math, so results agree to accumulation-order noise, and each stays
-    inside the bf16 budget against the generic CUDA path."""
+    """The two tile orders of the fused token kernel (serial, two-phase) are interchangeable: same TMEM-accumulated
+    math, so results agree to accumulation-order noise, and each stays inside the bf16 budget against the generic CUDA
+    path."""
     C, P, K, spatial, n = shape
     dims = synth.HeadDims(C, 256, P, K, spatial)
     sd = synth.make_head_params(dims, seed=77, bias_scale=0.05, last_layer_noise=0.1, bf16_round=True)
@@ -256,7 +304,7 @@ def test_token_kernel_variants_agree(shape):
     lib = _lib.load()
     outs = {}
     try:
-        for variant in (1, 2, 0, 3):
+        for variant in (1, 2):
             lib.pasn_debug_set_k1_variant(variant)
             outs[variant] = _run_all(m, xg)
             torch.cuda.synchronize()

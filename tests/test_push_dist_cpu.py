@@ -1,5 +1,6 @@
-"""world_size-2 gloo test (CPU) of the host-side push merge: packed-key all-reduce(MIN) with the unsigned-order
-sign flip, ownership by shard range, and the masked all-reduce(SUM) winner-row exchange."""
+"""world_size-2 gloo test (CPU) of the host-side push merge: ONE all-gather of the ranks' push records
+[keys | winner vectors], per-prototype minimum over the signed-order keys (ties -> lowest global index), and the
+keys-only all-reduce(MIN) helper."""
 import os
 
 import numpy as np
@@ -39,13 +40,21 @@ def _worker(rank, world, port, n_total, P, D, ret):
         key = key.view(np.uint64).copy()
         key[2] = _NONE                                                         # prototype 2: no candidate anywhere
         kt = torch.from_numpy(key.view(np.int64).copy())
-        pushmod.merge_keys(kt)
-        idx, dmin = pushmod.decode_keys(kt)
-        mine = (idx >= lo) & (idx < hi)
-        vec = torch.zeros(P, D)
-        for p in torch.nonzero(mine).flatten().tolist():
-            vec[p] = torch.from_numpy(feats[int(idx[p]), p])
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        # this rank's record: running keys + the pooled-feature row of each local winner (captured during the scan)
+        rec = pushmod.PushRecord(P, D, "cpu")
+        rec.key.copy_(kt)
+        idx_l, _ = pushmod.decode_keys(kt)
+        for p in range(P):
+            if int(idx_l[p]) >= 0:
+                rec.vec[p] = torch.from_numpy(feats[int(idx_l[p]), p])
+        gathered, R = pushmod.gather_records(rec)                              # the one collective
+        assert R == world and gathered.numel() == world * rec.buf.numel()
+        idx, dmin, valid, vec = pushmod.reduce_records(gathered, R, P, D)
+        k2 = kt.clone()
+        pushmod.merge_keys(k2)                                                 # keys-only helper agrees
+        idx2, dmin2 = pushmod.decode_keys(k2)
+        assert torch.equal(idx, idx2) and torch.equal(dmin, dmin2)
+        assert valid.tolist() == [int(i >= 0) for i in idx.tolist()]
         if rank == 0:
             ret["idx"], ret["d"], ret["vec"] = idx.numpy(), dmin.numpy(), vec.numpy()
             exp_idx = dmat.argmin(axis=0)
@@ -64,7 +73,7 @@ def test_two_rank_merge_gloo():
     assert ret["idx"][1] == 3                                   # cross-rank tie -> lowest global index
     ok = ret["exp_idx"] >= 0
     assert np.array_equal(ret["d"][ok], ret["exp_d"][ok]) and np.isinf(ret["d"][2])
-    assert np.array_equal(ret["vec"], ret["exp_vec"])           # masked SUM is exact
+    assert np.array_equal(ret["vec"], ret["exp_vec"])           # the winner's row travels with its key
 
 
 def test_shard_range_covers_set():

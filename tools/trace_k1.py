@@ -10,7 +10,7 @@ sd = synth.make_head_params(dims, seed=200, bias_scale=0.02, bf16_round=True)
 m = build_model(dims, sd, path=_lib.PASN_PATH_TCGEN05)
 x = torch.relu(torch.randn((1024, dims.C) + dims.spatial, device="cuda")).bfloat16()
 lib = _lib.load()
-buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     for _ in range(3):
         m(x)
@@ -18,7 +18,7 @@ with torch.no_grad():
     m(x)
     torch.cuda.synchronize()
     lib.pasn_debug_set_trace(None)
-t = buf.cpu().view(3, 16, 16)
+t = buf.cpu()[:768].view(3, 16, 16)
 t0 = int(t[0, 0, 0])
 if os.environ.get("PASN_K1_PHASES", "2") == "0":   # first-generation kernel
     names_m = ["start", "tmemfree", "L1issued", "g1ready", "G2issued", "g2ready", "Oissued", "osready", "hs0", "hs1", "poolissued"]
