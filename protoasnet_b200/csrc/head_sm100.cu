@@ -47,6 +47,7 @@ struct K2Params {
   const float* protos; const float* last_layer;
   float* logits; float* sim; float* dist; float* feats;
   const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
+  int a_kmajor, l2_hints;   // layout of the pooled-vector images (see K1Params::flush_kmajor); L2 eviction hints
   float* stash;   // push capture: [gridDim][P][256] fp32, FE row of this CTA's best clip per prototype (or null)
   int N, P, PP, K, cpt, ntiles;   // PP = padded P (row stride inside a tile), cpt = clips per tile = 128 / PP
   int* err;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     if (lane == 0) {
       griddep_wait();   // the pooled-vector images are written by the token kernel
       K2_TRACE(2);
+      const uint64_t pol_first = l2_policy_evict_first();
       uint32_t u = 0;
       bool ok = true;
       for (int it = 0; it < my_tiles && ok; ++it) {
@@ -131,8 +133,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
           if (!(ok = bwait(&bars[2 + s], ph ^ 1, ctx, 611))) break;
           const uint32_t dst = st_base + s * K2_STAGE;
           mbar_arrive_expect_tx(&bars[s], K2_STAGE);
-          bulk_g2s(dst, a_src + (size_t)kc * 16384, 16384, &bars[s]);
-          bulk_g2s(dst + 16384, a_src + 65536 + (size_t)kc * 16384, 16384, &bars[s]);
+          if (p.l2_hints) {   // the images were stored evict_last by the token kernel; read them once, then let them go
+            bulk_g2s_hint(dst, a_src + (size_t)kc * 16384, 16384, &bars[s], pol_first);
+            bulk_g2s_hint(dst + 16384, a_src + 65536 + (size_t)kc * 16384, 16384, &bars[s], pol_first);
+          } else {
+            bulk_g2s(dst, a_src + (size_t)kc * 16384, 16384, &bars[s]);
+            bulk_g2s(dst + 16384, a_src + 65536 + (size_t)kc * 16384, 16384, &bars[s]);
+          }
           bulk_g2s(dst + 32768, p.packed + p.off_w2 + (size_t)kc * 32768, 16384, &bars[s]);
           bulk_g2s(dst + 49152, p.packed + p.off_w2 + (size_t)kc * 32768 + 16384, 16384, &bars[s]);
         }
@@ -142,7 +149,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     // ---------------------------------------------------------------- MMA issuer (one elected thread, lean issue path:
     // see head_sm100_k1.cu -- descriptors as 32-bit halves in a single-thread region keep the UTCHMMAs back to back)
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, 256, 1, 0);  // A (pooled vectors) MN-major, B (W2) K-major
+      // A (pooled vectors): K-major rows (k = d contiguous) or MN-major images, B (W2) K-major
+      const uint32_t idesc = make_idesc_bf16(128, 256, p.a_kmajor ? 0 : 1, 0);
+      const uint32_t a_lbo = p.a_kmajor ? 16u : 8192u, a_kstep = p.a_kmajor ? 2u : 128u;
       constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
       const uint32_t bar0 = smem_u32(bars);
       uint32_t u = 0;
@@ -156,14 +165,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
           if (!(ok = bwait(&bars[s], ph, ctx, 622))) break;
           K2_TRACE(16 + it * 8 + kc);
           const uint32_t sb = st_base + s * K2_STAGE;
-          const uint32_t ah = desc_lo(sb, 8192), al = desc_lo(sb + 16384, 8192), bd = desc_lo(sb + 32768, 16);
+          const uint32_t ah = desc_lo(sb, a_lbo), al = desc_lo(sb + 16384, a_lbo), bd = desc_lo(sb + 32768, 16);
           const uint32_t d = tbase + 256u * buf;
           mma_ss_x(d, ah, HI, bd, HI, idesc, kc ? 1u : 0u);
           mma_ss_x(d, al, HI, bd, HI, idesc, 1u);
 #pragma unroll
           for (int k4 = 1; k4 < 4; ++k4) {
-            mma_ss_x(d, ah + k4 * 128, HI, bd + k4 * 2, HI, idesc, 1u);
-            mma_ss_x(d, al + k4 * 128, HI, bd + k4 * 2, HI, idesc, 1u);
+            mma_ss_x(d, ah + k4 * a_kstep, HI, bd + k4 * 2, HI, idesc, 1u);
+            mma_ss_x(d, al + k4 * a_kstep, HI, bd + k4 * 2, HI, idesc, 1u);
           }
           mma_commit_a(bar0 + 8u * (2 + s));
         }
@@ -496,6 +505,9 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.err = err;
   k1.trace = g_trace;
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
+  static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return e ? atoi(e) : 1; }();
+  static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 0; }();
+  k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
   const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
   // Token-kernel tile orders (same results; profiles/README.md): 1 = serial (default), 2 = two-phase
@@ -533,6 +545,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.ntiles = L.tiles2;
   k2.err = err;
   k2.trace = g_trace;
+  k2.a_kmajor = flush_kmajor; k2.l2_hints = l2_hints;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;   // <= K2_MAX_GRID
   {  // programmatic dependent launch: K2's prologue (TMEM, barriers, norms, the resident W2 images) overlaps K1's tail
     cudaLaunchConfig_t cfg{};

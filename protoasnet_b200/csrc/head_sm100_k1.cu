@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         while (pub < njobs) publish();
       }
     } else if (!p.f32_in) {
+      const uint64_t pol_first = l2_policy_evict_first();
       uint32_t pub = 0;
       auto publish = [&]() {
         fence_proxy_async();
@@ -521,9 +522,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
         const __nv_bfloat16* src = p.feat + ((size_t)rc * p.C + kc * 64 + xw * 16) * p.SR + (size_t)vg * S + s;
         const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
+        if (p.l2_hints) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u);
+          for (int j = 0; j < 16; ++j)
+            cp_async_8_hint(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u, pol_first);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u);
+        }
         cp_async_commit();
         if (g >= XDEPTH - 1) {
           cp_async_wait<XDEPTH - 1>();
@@ -657,6 +664,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
 #pragma unroll
     for (int i = 0; i < PP; ++i) facc[i] = 0.f;
     bool ok = true;
+    const uint64_t pol_last = l2_policy_evict_last();
 
     // acc_A^T half hh (128 voxel columns of this warp's 32 channel lanes) -> H1^T = relu(. + b1[d]) bf16, in place.
     // hh = 0 packs upwards into [256,320), hh = 1 downwards into [448,512): every store lands on columns whose fp32
@@ -844,24 +852,43 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
             continue;
           }
           const int clip = c_begin + (rep == 0 ? first_clip : last_clip);
-          // K2's A operand is MN-major (row = (clip,p) contiguous, k = d), so this thread's PP values for its d are
-          // PP/8 16-byte chunks per image: rows [rowb, rowb+PP) of k-chunk image d/64, hi at +0 and lo at +64 KB
           const int tile2 = clip / p.cpt;
           const int rowb = (clip - tile2 * p.cpt) * PP;
           uint8_t* img = p.feimg + (size_t)tile2 * FE_TILE_BYTES + (size_t)(d >> 6) * 16384;
+          if (p.flush_kmajor) {
+            // K2's A operand K-major (row = (clip,p), k = d contiguous): the 32 lanes of a warp hold 32 consecutive d of
+            // one row, i.e. 64 bytes inside one 128-byte swizzle row -> one line per warp store (hi at +0, lo at +64 KB)
 #pragma unroll
-          for (int c = 0; c < PP / 8; ++c) {
-            uint32_t hi4[4], lo4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float v0 = facc[8 * c + 2 * j], v1 = facc[8 * c + 2 * j + 1];
-              const float h0 = round_bf16(v0), h1 = round_bf16(v1);
-              hi4[j] = pack_bf16x2(h0, h1);
-              lo4[j] = pack_bf16x2(v0 - h0, v1 - h1);
+            for (int j = 0; j < PP; ++j) {
+              const float v = facc[j];
+              const __nv_bfloat16 h = __float2bfloat16_rn(v);
+              const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+              const uint32_t off = off_kmajor_sw128(rowb + j, d & 63);
+              if (p.l2_hints) {
+                st_global_u16_hint(img + off, __bfloat16_as_ushort(h), pol_last);
+                st_global_u16_hint(img + 65536 + off, __bfloat16_as_ushort(l), pol_last);
+              } else {
+                *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+                *reinterpret_cast<__nv_bfloat16*>(img + 65536 + off) = l;
+              }
             }
-            const uint32_t off = off_mnmajor_sw128(rowb + 8 * c, d & 63, 8192);
-            *reinterpret_cast<uint4*>(img + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-            *reinterpret_cast<uint4*>(img + 65536 + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          } else {
+            // K2's A operand MN-major (row = (clip,p) contiguous, k = d): this thread's PP values for its d are
+            // PP/8 16-byte chunks per image: rows [rowb, rowb+PP) of k-chunk image d/64, hi at +0 and lo at +64 KB
+#pragma unroll
+            for (int c = 0; c < PP / 8; ++c) {
+              uint32_t hi4[4], lo4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float v0 = facc[8 * c + 2 * j], v1 = facc[8 * c + 2 * j + 1];
+                const float h0 = round_bf16(v0), h1 = round_bf16(v1);
+                hi4[j] = pack_bf16x2(h0, h1);
+                lo4[j] = pack_bf16x2(v0 - h0, v1 - h1);
+              }
+              const uint32_t off = off_mnmajor_sw128(rowb + 8 * c, d & 63, 8192);
+              *reinterpret_cast<uint4*>(img + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+              *reinterpret_cast<uint4*>(img + 65536 + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            }
           }
           if (rep == 0) {
 #pragma unroll

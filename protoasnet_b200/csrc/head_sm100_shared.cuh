@@ -51,6 +51,9 @@ struct K1Params {
   int phases;                  // two-phase kernel: 2 = G / A phases overlapped with the previous chain, 1 = serial order
   int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X,
                                // bit3 = do not flush finished clips (head_sm100_k1.cu only)
+  int flush_kmajor;            // 1: finished clips leave as 2-byte stores into K-major SWIZZLE_128B operand images (one 128-byte
+                               // line per warp store); 0: 16-byte chunks of MN-major images (32 lines per warp store)
+  int l2_hints;                // 1: pooled-vector images are stored evict_last, the feature map is read evict_first
 };
 
 struct Ctx {

@@ -96,6 +96,29 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// L2 eviction-priority policies and hinted accesses (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_global_u16_hint(void* ptr, uint16_t v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(ptr), "h"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_8_hint(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint64_t policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(src_bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // arrive on `bar` (without bumping its pending count) once all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

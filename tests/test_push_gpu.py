@@ -266,8 +266,11 @@ def test_push_captures_winners_in_the_pass_that_saw_them(cfg, n, batch, tmp_path
     m = build_model(dims, sd)
     ds = _RandomWindowSet(x, labels)
     loader = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=False)
-    res = pushmod.push_prototypes(loader, m, root_dir_for_saving_prototypes=str(tmp_path), epoch_number="r", log=lambda *a: None)
+    before = m.prototype_vectors.data.clone()
+    res = pushmod.push_prototypes(loader, m, root_dir_for_saving_prototypes=str(tmp_path), epoch_number="r",
+                                  log=lambda *a: None, replace_prototypes=False)
     assert len(ds.handed) == n
+    assert torch.equal(m.prototype_vectors.data, before)
     idx = res["index"].cpu().numpy()
     assert (idx >= 0).all()
     info = pickle.load(open(os.path.join(str(tmp_path), "epoch-r", "prototypes_info.pickle"), "rb"))
@@ -276,7 +279,7 @@ def test_push_captures_winners_in_the_pass_that_saw_them(cfg, n, batch, tmp_path
         feats, dist, occ, logits = m.push_forward(drawn)          # row j = the clip that won prototype j, as drawn
     ar = torch.arange(dims.P, device="cuda")
     tol = 1e-5 if cfg == "tiny_video" else 1e-4                   # fused path: pooling order depends on the tile position
-    assert_close(m.prototype_vectors.data.reshape(dims.P, dims.D), feats[ar, ar].cpu().numpy(), tol, "prototype == drawn winner")
+    assert_close(res["features"], feats[ar, ar].cpu().numpy(), tol, "captured vector == pooled features of the drawn winner")
     assert_close(res["distance"], dist[ar, ar].cpu().numpy(), tol, "winner distance", atol_frac=tol)
     assert np.array_equal(info["prototypes_src_imgs"], drawn.cpu().numpy())
     assert_close(info["prototypes_occurrence_maps"], occ[ar, ar].float().cpu().numpy(), tol, "winner occurrence maps")
