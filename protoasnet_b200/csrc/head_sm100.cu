@@ -47,6 +47,8 @@ struct K2Params {
   const float* protos; const float* last_layer;
   float* logits; float* sim; float* dist; float* feats;
   const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
+  const int* ready;   // per-clip hand-off counters of the token kernel (null: wait for the whole grid instead)
+  int cpc;            // clips per token-kernel CTA (readiness order of the tiles)
   int a_kmajor, l2_hints;   // layout of the pooled-vector images (see K1Params::flush_kmajor); L2 eviction hints
   float* stash;   // push capture: [gridDim][P][256] fp32, FE row of this CTA's best clip per prototype (or null)
   int N, P, PP, K, cpt, ntiles;   // PP = padded P (row stride inside a tile), cpt = clips per tile = 128 / PP
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   float* s_part = reinterpret_cast<float*>(smem + K2_SM_MISC + 1536);          // [2][128][2] (dot, ff) of column half 1
   float* s_sim = reinterpret_cast<float*>(smem + K2_SM_MISC + 3584);           // [2][128]
   unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem + K2_SM_MISC + 4608);  // [64]
+  int* s_order = reinterpret_cast<int*>(smem + K2_SM_MISC + 5632);             // [64] this CTA's tiles in readiness order
+  int* s_tkey = reinterpret_cast<int*>(smem + K2_SM_MISC + 5888);              // [64]
   int* s_win = reinterpret_cast<int*>(smem + K2_SM_MISC + 5120);               // [128] push capture: row holds its prototype's best key
   float* s_v = reinterpret_cast<float*>(smem + K2_SM_V);
 
@@ -115,19 +119,57 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t st_base = smem_u32(smem);
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Tiles are taken in the order in which the token kernel finishes their clips (every token-kernel CTA walks its `cpc`
+  // clips in order, so a tile is ready once the latest position-in-range among its clips has been flushed): a CTA that
+  // starts while stragglers of the token kernel are still running works on finished tiles first.
+  const bool ordered = p.ready != nullptr && my_tiles <= 64;
+  if (ordered) {
+    if (tid < my_tiles) {
+      const int tile = blockIdx.x + tid * gridDim.x;
+      int c1 = tile * p.cpt + p.cpt;
+      if (c1 > p.N) c1 = p.N;
+      int key = 0;
+      for (int c = tile * p.cpt; c < c1; ++c) key = max(key, c % p.cpc);
+      s_tkey[tid] = key;
+    }
+    __syncthreads();
+    if (tid < my_tiles) {
+      int rank = 0;
+      const int mine = s_tkey[tid];
+      for (int j = 0; j < my_tiles; ++j) rank += (s_tkey[j] < mine || (s_tkey[j] == mine && j < tid)) ? 1 : 0;
+      s_order[rank] = tid;
+    }
+    __syncthreads();
+  }
+  auto tile_of = [&](int it) -> int { return blockIdx.x + (ordered ? s_order[it] : it) * gridDim.x; };
   if (tid == 0) K2_TRACE(1);   // prologue done
 
   if (warp == 9) {
     // ---------------------------------------------------------------- loader
     if (lane == 0) {
-      griddep_wait();   // the pooled-vector images are written by the token kernel
+      if (p.ready == nullptr) griddep_wait();   // the pooled-vector images are written by the token kernel
       K2_TRACE(2);
       const uint64_t pol_first = l2_policy_evict_first();
       uint32_t u = 0;
       bool ok = true;
       for (int it = 0; it < my_tiles && ok; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = tile_of(it);
         const uint8_t* a_src = p.feimg + (size_t)tile * FE_TILE_BYTES;
+        if (p.ready != nullptr) {
+          // clip-level hand-off: the token kernel bumps ready[clip] (release) once per epilogue warp and once for the
+          // Osum row; acquire here, then order the bulk (async-proxy) reads after it
+          int c1 = tile * p.cpt + p.cpt;
+          if (c1 > p.N) c1 = p.N;
+          const long long t0 = clock64();
+          for (int c = tile * p.cpt; c < c1 && ok; ++c) {
+            while (ld_acquire_gpu(p.ready + c) < K1_READY_TARGET) {
+              __nanosleep(100);
+              if (*abort_s || clock64() - t0 > 8000000000ll) { *abort_s = 1; atomicCAS(p.err, 0, 612); ok = false; break; }
+            }
+          }
+          if (!ok) break;
+          fence_proxy_async_all();
+        }
         for (int kc = 0; kc < 4; ++kc, ++u) {
           const uint32_t s = u & 1, ph = (u >> 1) & 1;
           if (!(ok = bwait(&bars[2 + s], ph ^ 1, ctx, 611))) break;
@@ -185,10 +227,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     const int q = warp & 3, ch = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane;
-    griddep_wait();   // Osum is written by the token kernel
+    if (p.ready == nullptr) griddep_wait();   // Osum is written by the token kernel
     bool ok = true;
     for (int it = 0; it < my_tiles && ok; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = tile_of(it);
       const uint32_t buf = it & 1;
       const int clip0 = tile * p.cpt;
       int nclip = p.N - clip0;
@@ -197,13 +239,16 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       const bool rvalid = cl_r < nclip && pp_r < p.P;
       const int cl = rvalid ? cl_r : 0, pp = rvalid ? pp_r : 0;
       const int n = clip0 + cl;
-      const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
       const float* vrow = s_v + pp * 257 + 128 * ch;
       const float* b2 = s_b2 + 128 * ch;
       float* frow = (p.feats && rvalid) ? p.feats + ((size_t)n * p.P + pp) * DD + 128 * ch : nullptr;
       if (!(ok = bwait(&bars[4 + buf], (it >> 1) & 1, ctx, 631))) break;
       tc_fence_after();
       if (tid == 0) K2_TRACE(16 + it * 8 + 5);
+      // the loader has seen this tile's clips handed over (the accumulator could not be full otherwise); acquire again
+      // in this thread before touching the Osum row the token kernel wrote
+      if (p.ready != nullptr && rvalid) (void)ld_acquire_gpu(p.ready + n);
+      const float os = rvalid ? p.osum[(size_t)n * p.P + pp] : 0.f;
       const uint32_t ta = tbase + lane_base + 256u * buf + 128u * ch;
       float ff = 0.f, dot = 0.f;
       uint32_t ra[32], rb[32];
@@ -421,7 +466,7 @@ static inline int split_groups(const pasn_dims& d) {
 constexpr int K2_MAX_GRID = 160;   // upper bound of K2's grid (one CTA per SM)
 struct WsLayout {
   int G, Nv, Sv, tiles2;
-  size_t off_osum, off_err, off_stash, off_featsv, off_fe, off_simv, off_logv, total;
+  size_t off_osum, off_err, off_ready, off_stash, off_featsv, off_fe, off_simv, off_logv, total;
 };
 static inline WsLayout ws_layout(const pasn_dims& d) {
   WsLayout L;
@@ -432,6 +477,7 @@ static inline WsLayout ws_layout(const pasn_dims& d) {
   size_t o = (size_t)L.tiles2 * FE_TILE_BYTES;
   L.off_osum = o; o += align_up((size_t)L.Nv * d.P * 4, 256);
   L.off_err = o; o += 256;
+  L.off_ready = o; o += align_up((size_t)L.Nv * 4, 256);   // directly behind err: one memset clears both
   L.off_stash = o; o += align_up((size_t)K2_MAX_GRID * d.P * DD * 4, 256);   // push capture: FE row of each K2 CTA's best clip per prototype
   L.off_featsv = L.off_fe = L.off_simv = L.off_logv = o;
   if (L.G > 1) {
@@ -482,7 +528,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   uint8_t* feimg = reinterpret_cast<uint8_t*>(wsp);
   float* osum = reinterpret_cast<float*>(wsp + L.off_osum);
   int* err = reinterpret_cast<int*>(wsp + L.off_err);
-  if (cudaMemsetAsync(err, 0, 4, st) != cudaSuccess) return PASN_ERR_CUDA;
+  int* ready = reinterpret_cast<int*>(wsp + L.off_ready);
+  if (cudaMemsetAsync(err, 0, 256 + (size_t)L.Nv * 4, st) != cudaSuccess) return PASN_ERR_CUDA;
 
   static const int num_sms = [] {
     int dev = 0, n = 0;
@@ -506,8 +553,10 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.trace = g_trace;
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
   static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return e ? atoi(e) : 1; }();
-  static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 0; }();
+  static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 1; }();
   k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
+  static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 1; }();
+  k1.ready = ready;
   const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
   // Token-kernel tile orders (same results; profiles/README.md): 1 = serial (default), 2 = two-phase
@@ -546,6 +595,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.err = err;
   k2.trace = g_trace;
   k2.a_kmajor = flush_kmajor; k2.l2_hints = l2_hints;
+  k2.ready = k2_early ? ready : nullptr; k2.cpc = k1.clips_per_cta;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;   // <= K2_MAX_GRID
   {  // programmatic dependent launch: K2's prologue (TMEM, barriers, norms, the resident W2 images) overlaps K1's tail
     cudaLaunchConfig_t cfg{};

@@ -644,11 +644,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         if (lane < p.P) p.osum[(size_t)(c_begin + first_clip) * p.P + lane] = acc0;
         if (lane + 32 < p.P) p.osum[(size_t)(c_begin + first_clip) * p.P + lane + 32] = acc1;
         acc0 = s0[1]; acc1 = s1[1];
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(p.ready + c_begin + first_clip, 1);
       }
       if ((last_tok + 1) % S == 0) {
         if (lane < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane] = acc0;
         if (lane + 32 < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane + 32] = acc1;
         acc0 = acc1 = 0.f;
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(p.ready + c_begin + last_clip, 1);
       }
     }
   } else if (warp >= W_EPI0) {
@@ -842,6 +846,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           const bool flush = rep == 0 ? boundary : ends;
           if (!flush) continue;
           if (p.dbg_skip & 8) {   // timing experiment: no hi/lo split, no stores (results garbage)
+            if (lane == 0) red_release_gpu_add(p.ready + c_begin + (rep == 0 ? first_clip : last_clip), 1);
             if (rep == 0) {
 #pragma unroll
               for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);
@@ -890,6 +895,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
               *reinterpret_cast<uint4*>(img + 65536 + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
             }
           }
+          // hand the clip to the prototype kernel (it polls the counter; see proto_w2_kernel)
+          __syncwarp();
+          if (lane == 0) red_release_gpu_add(p.ready + clip, 1);
           if (rep == 0) {
 #pragma unroll
             for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);

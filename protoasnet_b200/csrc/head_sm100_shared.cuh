@@ -12,6 +12,7 @@ constexpr int TILE_M = 128;
 constexpr int DD = 256;            // prototype depth D handled by this kernel
 constexpr int DH = DD / 2;         // occurrence hidden width
 constexpr int PP_MAX = 48;         // padded prototype count limit (multiple of 8)
+constexpr int K1_READY_TARGET = 9;  // 8 epilogue warps + the occurrence warp
 constexpr uint32_t FE_TILE_BYTES = 131072;  // K2 operand images of one 128-row tile: hi 64 KB | lo 64 KB
 
 // packed weight buffer (bf16 stage images + fp32 biases), see pack_weights_kernel
@@ -53,6 +54,8 @@ struct K1Params {
                                // bit3 = do not flush finished clips (head_sm100_k1.cu only)
   int flush_kmajor;            // 1: finished clips leave as 2-byte stores into K-major SWIZZLE_128B operand images (one 128-byte
                                // line per warp store); 0: 16-byte chunks of MN-major images (32 lines per warp store)
+  int* ready;                  // [N] per-clip hand-off counter to the prototype kernel: +1 per epilogue warp that has stored
+                               // its part of the clip's pooled vectors, +1 for the clip's Osum row (K1_READY_TARGET in total)
   int l2_hints;                // 1: pooled-vector images are stored evict_last, the feature map is read evict_first
 };
 
