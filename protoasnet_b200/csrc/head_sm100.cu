@@ -48,7 +48,9 @@ struct K2Params {
   float* logits; float* sim; float* dist; float* feats;
   const int64_t* labels; const int32_t* proto_class; long long global_offset; unsigned long long* best_key;
   const int* ready;   // per-clip hand-off counters of the token kernel (null: wait for the whole grid instead)
-  int cpc;            // clips per token-kernel CTA (readiness order of the tiles)
+  int cpc, grid1;     // clips per token-kernel CTA and its grid (readiness order of the tiles)
+  int* queue;         // dynamic tile queue counter (zeroed per call)
+  int* tile_owner;    // [ntiles] CTA that processed a tile (push capture)
   int a_kmajor, l2_hints;   // layout of the pooled-vector images (see K1Params::flush_kmajor); L2 eviction hints
   float* stash;   // push capture: [gridDim][P][256] fp32, FE row of this CTA's best clip per prototype (or null)
   int N, P, PP, K, cpt, ntiles;   // PP = padded P (row stride inside a tile), cpt = clips per tile = 128 / PP
@@ -73,8 +75,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   float* s_part = reinterpret_cast<float*>(smem + K2_SM_MISC + 1536);          // [2][128][2] (dot, ff) of column half 1
   float* s_sim = reinterpret_cast<float*>(smem + K2_SM_MISC + 3584);           // [2][128]
   unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem + K2_SM_MISC + 4608);  // [64]
-  int* s_order = reinterpret_cast<int*>(smem + K2_SM_MISC + 5632);             // [64] this CTA's tiles in readiness order
-  int* s_tkey = reinterpret_cast<int*>(smem + K2_SM_MISC + 5888);              // [64]
+  uint64_t* tbars = reinterpret_cast<uint64_t*>(smem + K2_SM_MISC + 5632);     // [4] tile-info slots published by the loader
+  volatile int* s_tile = reinterpret_cast<volatile int*>(smem + K2_SM_MISC + 5696);   // [4] tile index or -1 (no more tiles)
   int* s_win = reinterpret_cast<int*>(smem + K2_SM_MISC + 5120);               // [128] push capture: row holds its prototype's best key
   float* s_v = reinterpret_cast<float*>(smem + K2_SM_V);
 
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     *abort_s = 0;
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
     mbar_init(&bars[4], 1); mbar_init(&bars[5], 1); mbar_init(&bars[6], 8); mbar_init(&bars[7], 8);
+    for (int i = 0; i < 4; ++i) mbar_init(&tbars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_s, 512);
@@ -118,30 +121,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t st_base = smem_u32(smem);
-  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // Tiles are taken in the order in which the token kernel finishes their clips (every token-kernel CTA walks its `cpc`
-  // clips in order, so a tile is ready once the latest position-in-range among its clips has been flushed): a CTA that
-  // starts while stragglers of the token kernel are still running works on finished tiles first.
-  const bool ordered = p.ready != nullptr && my_tiles <= 64;
-  if (ordered) {
-    if (tid < my_tiles) {
-      const int tile = blockIdx.x + tid * gridDim.x;
-      int c1 = tile * p.cpt + p.cpt;
-      if (c1 > p.N) c1 = p.N;
-      int key = 0;
-      for (int c = tile * p.cpt; c < c1; ++c) key = max(key, c % p.cpc);
-      s_tkey[tid] = key;
-    }
-    __syncthreads();
-    if (tid < my_tiles) {
-      int rank = 0;
-      const int mine = s_tkey[tid];
-      for (int j = 0; j < my_tiles; ++j) rank += (s_tkey[j] < mine || (s_tkey[j] == mine && j < tid)) ? 1 : 0;
-      s_order[rank] = tid;
-    }
-    __syncthreads();
-  }
-  auto tile_of = [&](int it) -> int { return blockIdx.x + (ordered ? s_order[it] : it) * gridDim.x; };
+  // Tile hand-out.  With the clip-level hand-off (p.ready) tiles come from a global queue in the order in which the token
+  // kernel finishes their clips: every token-kernel CTA walks its `cpc` clips in order, so queue slot i stands for clip
+  // (i % grid1) * cpc + i / grid1, and a tile is handed out at the slot of its latest clip.  A CTA that becomes resident
+  // while stragglers of the token kernel are still running thus works on finished tiles, and late CTAs take fewer.
+  // Without it (PASN_K2_EARLY=0) the tiles are dealt round-robin after the whole token kernel has completed.
+  // The loader publishes each tile index (or -1) in a 4-slot ring guarded by mbarriers; MMA issuer and epilogue follow.
+  const bool dynamic = p.ready != nullptr;
   if (tid == 0) K2_TRACE(1);   // prologue done
 
   if (warp == 9) {
@@ -152,8 +138,32 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       const uint64_t pol_first = l2_policy_evict_first();
       uint32_t u = 0;
       bool ok = true;
-      for (int it = 0; it < my_tiles && ok; ++it) {
-        const int tile = tile_of(it);
+      for (int it = 0; ok; ++it) {
+        int tile = -1;
+        if (dynamic) {
+          const int nslots = p.grid1 * p.cpc;
+          for (;;) {
+            const int i = atomicAdd(p.queue, 1);
+            if (i >= nslots) break;
+            const int rnd = i / p.grid1, clip = (i - rnd * p.grid1) * p.cpc + rnd;
+            if (clip >= p.N) continue;
+            const int t = clip / p.cpt, c0 = t * p.cpt;
+            int c1 = c0 + p.cpt;
+            if (c1 > p.N) c1 = p.N;
+            int key = 0;
+            for (int c = c0; c < c1; ++c) key = max(key, c % p.cpc);
+            int first = c0;
+            while (first % p.cpc != key) ++first;
+            if (clip == first) { tile = t; break; }
+          }
+        } else {
+          tile = (int)blockIdx.x + it * (int)gridDim.x;
+          if (tile >= p.ntiles) tile = -1;
+        }
+        s_tile[it & 3] = tile;
+        mbar_arrive(&tbars[it & 3]);
+        if (tile < 0) break;
+        if (p.tile_owner != nullptr) p.tile_owner[tile] = (int)blockIdx.x;
         const uint8_t* a_src = p.feimg + (size_t)tile * FE_TILE_BYTES;
         if (p.ready != nullptr) {
           // clip-level hand-off: the token kernel bumps ready[clip] (release) once per epilogue warp and once for the
@@ -198,7 +208,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       const uint32_t bar0 = smem_u32(bars);
       uint32_t u = 0;
       bool ok = true;
-      for (int it = 0; it < my_tiles && ok; ++it) {
+      for (int it = 0; ok; ++it) {
+        if (!(ok = bwait(&tbars[it & 3], (it >> 2) & 1, ctx, 623))) break;
+        if (s_tile[it & 3] < 0) break;
         const uint32_t buf = it & 1;
         if (!(ok = bwait(&bars[6 + buf], ((it >> 1) & 1) ^ 1, ctx, 621))) break;
         tc_fence_after();
@@ -229,8 +241,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
     const int r = q * 32 + lane;
     if (p.ready == nullptr) griddep_wait();   // Osum is written by the token kernel
     bool ok = true;
-    for (int it = 0; it < my_tiles && ok; ++it) {
-      const int tile = tile_of(it);
+    for (int it = 0; ok; ++it) {
+      if (!(ok = bwait(&tbars[it & 3], (it >> 2) & 1, ctx, 632))) break;
+      const int tile = s_tile[it & 3];
+      if (tile < 0) break;
       const uint32_t buf = it & 1;
       const int clip0 = tile * p.cpt;
       int nclip = p.N - clip0;
@@ -408,13 +422,15 @@ __global__ void pack_weights_kernel(pasn_weights w, int C, int P, uint8_t* out) 
 // to this call (keys carry the global clip index).  One block per prototype.
 // =================================================================================================
 __global__ void push_capture_stash_kernel(const unsigned long long* __restrict__ best_key, int P, long long offset, int N,
-                                          int cpt, int grid2, const float* __restrict__ stash, float* __restrict__ best_vec) {
+                                          int cpt, int grid2, const int* __restrict__ tile_owner, const float* __restrict__ stash,
+                                          float* __restrict__ best_vec) {
   const int pp = blockIdx.x;
   const unsigned long long key = best_key[pp] ^ PASN_KEY_SIGN;
   if (key == PASN_KEY_NONE) return;
   const long long idx = (long long)(key & 0xFFFFFFFFull);
   if (idx < offset || idx >= offset + N) return;
-  const int cta = (int)((idx - offset) / cpt) % grid2;
+  const int tile = (int)((idx - offset) / cpt);
+  const int cta = tile_owner != nullptr ? tile_owner[tile] : tile % grid2;
   const float* src = stash + ((size_t)cta * P + pp) * DD;
   for (int d = threadIdx.x; d < DD; d += blockDim.x) best_vec[(size_t)pp * DD + d] = src[d];
 }
@@ -466,7 +482,7 @@ static inline int split_groups(const pasn_dims& d) {
 constexpr int K2_MAX_GRID = 160;   // upper bound of K2's grid (one CTA per SM)
 struct WsLayout {
   int G, Nv, Sv, tiles2;
-  size_t off_osum, off_err, off_ready, off_stash, off_featsv, off_fe, off_simv, off_logv, total;
+  size_t off_osum, off_err, off_ready, off_owner, off_stash, off_featsv, off_fe, off_simv, off_logv, total;
 };
 static inline WsLayout ws_layout(const pasn_dims& d) {
   WsLayout L;
@@ -478,6 +494,7 @@ static inline WsLayout ws_layout(const pasn_dims& d) {
   L.off_osum = o; o += align_up((size_t)L.Nv * d.P * 4, 256);
   L.off_err = o; o += 256;
   L.off_ready = o; o += align_up((size_t)L.Nv * 4, 256);   // directly behind err: one memset clears both
+  L.off_owner = o; o += align_up((size_t)L.tiles2 * 4, 256);
   L.off_stash = o; o += align_up((size_t)K2_MAX_GRID * d.P * DD * 4, 256);   // push capture: FE row of each K2 CTA's best clip per prototype
   L.off_featsv = L.off_fe = L.off_simv = L.off_logv = o;
   if (L.G > 1) {
@@ -595,7 +612,9 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.err = err;
   k2.trace = g_trace;
   k2.a_kmajor = flush_kmajor; k2.l2_hints = l2_hints;
-  k2.ready = k2_early ? ready : nullptr; k2.cpc = k1.clips_per_cta;
+  k2.ready = k2_early ? ready : nullptr; k2.cpc = k1.clips_per_cta; k2.grid1 = grid1;
+  k2.queue = err + 1;
+  k2.tile_owner = k2_early ? reinterpret_cast<int*>(wsp + L.off_owner) : nullptr;
   const int grid2 = k2.ntiles < num_sms ? k2.ntiles : num_sms;   // <= K2_MAX_GRID
   {  // programmatic dependent launch: K2's prologue (TMEM, barriers, norms, the resident W2 images) overlaps K1's tail
     cudaLaunchConfig_t cfg{};
@@ -609,7 +628,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   PASN_LAUNCH_CHECK();
   count_launch();
   if (k2.stash) {
-    push_capture_stash_kernel<<<d.P, 128, 0, st>>>(k2.best_key, d.P, k2.global_offset, L.Nv, k2.cpt, grid2, k2.stash, push->best_vec);
+    push_capture_stash_kernel<<<d.P, 128, 0, st>>>(k2.best_key, d.P, k2.global_offset, L.Nv, k2.cpt, grid2, k2.tile_owner, k2.stash,
+                                                   push->best_vec);
     PASN_LAUNCH_CHECK();
     count_launch();
   }

@@ -1,0 +1,414 @@
+// Persistent, warp-specialised tcgen05 GEMM (see tc_gemm.cuh for the operation).
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor (tensor maps, SWIZZLE_128B) into a 3-stage ring of
+//               [A 128x64 | B bn x 64] bf16 operand tiles; out-of-range rows / k are zero-filled by the TMA unit
+//   warp 1      MMA issuer: one elected thread, tcgen05.mma kind::f16 M128 x N(bn) x K16, fp32 accumulators in TMEM,
+//               two accumulator buffers of 256 columns so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2      TMEM allocation
+//   warps 4-11  epilogue: warp w reads TMEM lanes 32*(w%4).. (its 32 rows) of column half w/4, applies
+//               bias / rank-1 term / ReLU / abs, converts, and leaves the rows either through a private swizzled
+//               staging slab + TMA store (16-byte aligned outputs) or with plain stores (small unaligned outputs)
+//
+// Every mbarrier wait is bounded: a protocol fault becomes an error code in *err, not a hung GPU.
+#include <cuda.h>
+
+#include "sm100_prims.cuh"
+#include "tc_gemm.cuh"
+
+namespace pasn {
+namespace tcg {
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES_MAX = 256 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES_MAX;   // 48 KB
+constexpr int EPI_WARPS = 8, EPI_WARP0 = 4, THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+constexpr uint32_t SLAB_BYTES = 4096;                             // 32 rows x 128 bytes
+constexpr uint32_t SM_STG = STAGES * STAGE_BYTES;                 // 147456: staging slabs, 2 per epilogue warp
+constexpr uint32_t SM_VEC = SM_STG + EPI_WARPS * 2 * SLAB_BYTES;  // 212992: per-warp bias / colvec slices (2 x 64 floats)
+constexpr uint32_t SM_BAR = SM_VEC + EPI_WARPS * 512;             // 217088
+constexpr uint32_t SM_MISC = SM_BAR + 16 * 8;
+constexpr uint32_t SMEM_BYTES = SM_MISC + 64;
+enum { B_FULL = 0, B_EMPTY = STAGES, B_ACCFULL = 2 * STAGES, B_ACCEMPTY = 2 * STAGES + 2 };
+
+struct alignas(64) KParams {
+  CUtensorMap tmA, tmB, tmO[4];   // out0 (hi), out0 lo, out1 (hi), out1 lo
+  Gemm g;
+  int out_tma[2];
+  int tiles_m, tiles_n, nkb;
+  int* err;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
+
+static __device__ __noinline__ bool wait_slow(uint64_t* bar, uint32_t parity, int* err, int code) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      atomicCAS(err, 0, code);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return wait_slow(bar, parity, err, code);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  return act == ACT_RELU ? fmaxf(v, 0.f) : (act == ACT_ABS ? fabsf(v) : v);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ KParams kp) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+  const Gemm& g = kp.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) atomicCAS(kp.err, 0, 700);
+    return;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_ACCFULL + i], 1); mbar_init(&bars[B_ACCEMPTY + i], EPI_WARPS); }
+    fence_mbar_init();
+    prefetch_tmap(&kp.tmA);
+    prefetch_tmap(&kp.tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr_s;
+  const uint32_t sbase = smem_u32(smem);
+  const int bn = g.bn;
+  const int tiles_per_batch = kp.tiles_m * kp.tiles_n;
+  const int ntiles = g.batch * tiles_per_batch;
+  const int nk = g.npass * kp.nkb;   // k-blocks per tile
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t s = 0, ph = 0;
+      bool ok = true;
+      const uint32_t stage_tx = A_BYTES + (uint32_t)bn * 128u;
+      for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
+        const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
+        const int m0 = (r / kp.tiles_n) * BM, n0 = (r % kp.tiles_n) * bn;
+        for (int pass = 0; pass < g.npass && ok; ++pass) {
+          for (int kb = 0; kb < kp.nkb; ++kb) {
+            if (!(ok = bwait(&bars[B_EMPTY + s], ph ^ 1, kp.err, 701))) break;
+            const uint32_t dst = sbase + s * STAGE_BYTES;
+            mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
+            tma_load_3d(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
+            if (!g.b_mn_major) {
+              tma_load_3d(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
+            } else {
+              for (int j = 0; j < bn / 64; ++j)
+                tma_load_3d(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, kb * BK, g.b_batched ? b : 0,
+                            &bars[B_FULL + s]);
+            }
+            s = s + 1 == STAGES ? 0 : s + 1;
+            ph ^= (s == 0) ? 1u : 0u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)bn, 0, g.b_mn_major ? 1u : 0u);
+      constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
+      const uint32_t b_lbo = g.b_mn_major ? 8192u : 16u, b_kstep = g.b_mn_major ? 128u : 2u;
+      const uint32_t bar0 = smem_u32(bars);
+      uint32_t s = 0, ph = 0;
+      bool ok = true;
+      int i = 0;
+      for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1;
+        if (!(ok = bwait(&bars[B_ACCEMPTY + buf], ((i >> 1) & 1) ^ 1, kp.err, 711))) break;
+        tc_fence_after();
+        const uint32_t d = tbase + 256u * buf;
+        for (int kk = 0; kk < nk; ++kk) {
+          if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
+          tc_fence_after();
+          const uint32_t sa = sbase + s * STAGE_BYTES;
+          const uint32_t alo = desc_lo(sa, 16), blo = desc_lo(sa + A_BYTES, b_lbo);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * 2, HI, blo + k4 * b_kstep, HI, idesc, (kk | k4) ? 1u : 0u);
+          mma_commit_a(bar0 + 8u * (B_EMPTY + s));
+          s = s + 1 == STAGES ? 0 : s + 1;
+          ph ^= (s == 0) ? 1u : 0u;
+        }
+        if (ok) mma_commit_a(bar0 + 8u * (B_ACCFULL + buf));
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue
+    const int w = warp - EPI_WARP0, q = w & 3, h = w >> 2;
+    const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
+    const uint32_t slab0 = sbase + SM_STG + (uint32_t)w * 2u * SLAB_BYTES;
+    float* vecs = reinterpret_cast<float*>(smem + SM_VEC + w * 512);   // [0,64) bias slice, [64,128) colvec slice
+    const int half_cols = bn / 2;
+    const int ngroups = (half_cols + 63) / 64;
+    uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
+    bool ok = true;
+    int i = 0;
+    // one 64-column group of one output leaves through the staging slab(s) + TMA store(s)
+    auto store_tma = [&](const Output& o, int mi, const float (&v)[64], int col0, int row0, int b) {
+      const int nbox = o.mode == OUT_BF16 ? 1 : 2;
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx) {
+        if (bx >= nbox) break;
+        if (lane == 0) bulk_wait_read<1>();   // the slab used two stores ago has been read out
+        __syncwarp();
+        const uint32_t slab = slab0 + (nstores & 1u) * SLAB_BYTES;
+        const uint32_t rowaddr = slab + (uint32_t)lane * 128u;
+        if (o.mode == OUT_F32) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[32 * bx + 4 * c]), "f"(v[32 * bx + 4 * c + 1]),
+                         "f"(v[32 * bx + 4 * c + 2]), "f"(v[32 * bx + 4 * c + 3])
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
+              if (o.mode == OUT_BF16_HILO && bx == 1) { a0 -= round_bf16(a0); a1 -= round_bf16(a1); }
+              pk[j] = pack_bf16x2(a0, a1);
+            }
+            const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = o.mode == OUT_F32 ? col0 + 32 * bx : col0;
+          const CUtensorMap* map = &kp.tmO[2 * mi + ((o.mode == OUT_BF16_HILO && bx == 1) ? 1 : 0)];
+          tma_store_3d(map, slab, c0, row0, b);
+          bulk_commit();
+        }
+        ++nstores;
+      }
+    };
+    auto store_direct = [&](const Output& o, const float (&v)[64], int col0, int row, int b, bool row_ok) {
+      if (!row_ok) return;
+      const long long base = (long long)b * o.bs + (long long)row * o.ld;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int col = col0 + j;
+        if (col >= g.N) continue;
+        if (o.mode == OUT_F32) {
+          reinterpret_cast<float*>(o.ptr)[base + col] = v[j];
+        } else {
+          __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+          p16[base + col] = hi;
+          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+        }
+      }
+    };
+
+    for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++i) {
+      const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
+      const int tn = r % kp.tiles_n;
+      const int m0 = (r / kp.tiles_n) * BM, n0 = tn * bn;
+      const uint32_t buf = i & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      float rowterm = 0.f;
+      if (g.rowparts != nullptr && row_ok) {
+        const float* rp = g.rowparts + ((size_t)b * g.M + row) * g.nparts;
+        for (int j = 0; j < g.nparts; ++j) rowterm += rp[j];
+      }
+      float psum = 0.f;
+      if (!(ok = bwait(&bars[B_ACCFULL + buf], (i >> 1) & 1, kp.err, 721))) break;
+      tc_fence_after();
+      for (int cg = 0; cg < ngroups; ++cg) {
+        const int cl = h * half_cols + 64 * cg;       // column inside the tile
+        const int col0 = n0 + cl;
+        // bias / colvec slices of this group -> per-warp smem (broadcast reads below)
+        __syncwarp();
+        for (int j = lane; j < 64; j += 32) {
+          const int col = col0 + j;
+          vecs[j] = (g.bias != nullptr && col < g.N) ? g.bias[col] : 0.f;
+          vecs[64 + j] = (g.colvec != nullptr && col < g.N) ? g.colvec[col] : 0.f;
+        }
+        __syncwarp();
+        float v[64];
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(tl + 256u * buf + (uint32_t)cl, ra);
+          if (half_cols - 64 * cg > 32) tmem_ld_x32(tl + 256u * buf + (uint32_t)cl + 32u, rb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(ra[j]); v[32 + j] = __uint_as_float(rb[j]); }
+        }
+        if (cg == ngroups - 1) {   // all TMEM reads of this tile are done: hand the accumulator back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 bb = *reinterpret_cast<const float4*>(vecs + 4 * j4);
+          const float4 cc = *reinterpret_cast<const float4*>(vecs + 64 + 4 * j4);
+          v[4 * j4 + 0] = act_apply(fmaf(rowterm, cc.x, v[4 * j4 + 0] + bb.x), g.act);
+          v[4 * j4 + 1] = act_apply(fmaf(rowterm, cc.y, v[4 * j4 + 1] + bb.y), g.act);
+          v[4 * j4 + 2] = act_apply(fmaf(rowterm, cc.z, v[4 * j4 + 2] + bb.z), g.act);
+          v[4 * j4 + 3] = act_apply(fmaf(rowterm, cc.w, v[4 * j4 + 3] + bb.w), g.act);
+        }
+        if (g.psum != nullptr) {
+          const bool rounded = g.out[0].mode == OUT_BF16;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) psum += (col0 + j < g.N) ? (rounded ? round_bf16(v[j]) : v[j]) : 0.f;
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const Output& o = g.out[mi];
+          if (o.mode == OUT_NONE) continue;
+          if (kp.out_tma[mi]) store_tma(o, mi, v, col0, m0 + q * 32, b);
+          else store_direct(o, v, col0, row, b, row_ok);
+        }
+      }
+      if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = psum;
+    }
+    if (lane == 0) bulk_wait<0>();   // outstanding TMA stores must complete before the CTA's smem goes away
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tbase, 512);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+// 3-D map over [d2][d1][d0] (d0 innermost), strides in bytes, box {b0, b1, 1}
+bool make_map(CUtensorMap* m, CUtensorMapDataType dt, int elt, const void* base, unsigned long long d0, unsigned long long d1,
+              unsigned long long d2, unsigned long long s1_bytes, unsigned long long s2_bytes, unsigned b0, unsigned b1) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  if (((uintptr_t)base & 15) != 0 || (s1_bytes & 15) != 0 || (s2_bytes & 15) != 0) return false;
+  cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes ? s2_bytes : s1_bytes * d1};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  (void)elt;
+  return fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool out_aligned(const Output& o) {
+  const int elt = o.mode == OUT_F32 ? 4 : 2;
+  if (((uintptr_t)o.ptr & 15) != 0 || ((o.ld * elt) & 15) != 0 || ((o.bs * elt) & 15) != 0) return false;
+  if (o.mode == OUT_BF16_HILO && ((o.lo_off * elt) & 15) != 0) return false;
+  return true;
+}
+}  // namespace
+
+bool available() { return encode_fn() != nullptr; }
+
+int launch(const Gemm& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;
+  if (g.npass < 1 || g.npass > 3 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
+  static int* d_err = nullptr;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+      return PASN_ERR_CUDA;
+    if (cudaMalloc(&d_err, 256) != cudaSuccess) return PASN_ERR_CUDA;   // one-time, 256-byte fault word (never freed)
+    if (cudaMemset(d_err, 0, 256) != cudaSuccess) return PASN_ERR_CUDA;
+    attr_done = true;
+  }
+  KParams kp;
+  kp.g = g;
+  kp.err = d_err;
+  kp.tiles_m = ceil_div(g.M, BM);
+  kp.tiles_n = ceil_div(g.N, g.bn);
+  kp.nkb = ceil_div(g.K, BK);
+  if (!make_map(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, (unsigned long long)g.ka, (unsigned long long)g.M,
+                g.a_batched ? g.batch : 1, (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, BK, BM))
+    return PASN_ERR_ALIGN;
+  if (!g.b_mn_major) {
+    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb, (unsigned long long)g.N,
+                  g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)g.bn))
+      return PASN_ERR_ALIGN;
+  } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
+    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb, (unsigned long long)g.K,
+                  g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
+      return PASN_ERR_ALIGN;
+  }
+  for (int mi = 0; mi < 2; ++mi) {
+    const Output& o = g.out[mi];
+    kp.out_tma[mi] = 0;
+    kp.tmO[2 * mi] = kp.tmA;
+    kp.tmO[2 * mi + 1] = kp.tmA;
+    if (o.mode == OUT_NONE || !out_aligned(o)) continue;
+    const bool f32 = o.mode == OUT_F32;
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const int elt = f32 ? 4 : 2;
+    bool okm = make_map(&kp.tmO[2 * mi], dt, elt, o.ptr, (unsigned long long)g.N, (unsigned long long)g.M, g.batch,
+                        (unsigned long long)o.ld * elt, (unsigned long long)o.bs * elt, f32 ? 32 : 64, 32);
+    if (okm && o.mode == OUT_BF16_HILO)
+      okm = make_map(&kp.tmO[2 * mi + 1], dt, elt, reinterpret_cast<const char*>(o.ptr) + (size_t)o.lo_off * 2,
+                     (unsigned long long)g.N, (unsigned long long)g.M, g.batch, (unsigned long long)o.ld * elt,
+                     (unsigned long long)o.bs * elt, 64, 32);
+    kp.out_tma[mi] = okm ? 1 : 0;
+  }
+  static const int num_sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
+  }();
+  const long long ntiles = (long long)g.batch * kp.tiles_m * kp.tiles_n;
+  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(kp);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+
+}  // namespace tcg
+}  // namespace pasn
