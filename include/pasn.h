@@ -49,9 +49,11 @@ typedef enum { PASN_OCC_ABS = 0 } pasn_occ_act;
 
 /* which kernel family computes the head */
 typedef enum {
-  PASN_PATH_AUTO = 0,    /* tcgen05 when dims/dtype qualify, else generic                    */
-  PASN_PATH_GENERIC = 1, /* CUDA-core FFMA kernels, fp32 accumulate, every shape/dtype       */
-  PASN_PATH_TCGEN05 = 2  /* fused tcgen05/TMEM kernel (bf16 operands, fp32 accumulate)       */
+  PASN_PATH_AUTO = 0,    /* fused kernel when dims/dtype qualify, else tiled, else generic                      */
+  PASN_PATH_GENERIC = 1, /* CUDA-core FFMA kernels, fp32 accumulate, every shape/dtype                          */
+  PASN_PATH_TCGEN05 = 2, /* fused tcgen05/TMEM token kernel (bf16 operands, fp32 accumulate; D = 256, S >= 128) */
+  PASN_PATH_TILED = 3    /* chain of TMA-fed tcgen05 GEMMs: any S / P, D % 128 == 0, C % 64 == 0; bf16 feature   */
+                         /* maps in bf16, fp32 feature maps as a 3-pass bf16 hi/lo split (fp32-grade results)   */
 } pasn_path;
 
 typedef struct {
@@ -107,20 +109,21 @@ typedef struct {
 int pasn_abi_version(void);
 const char* pasn_strerror(int status);
 
-/* 1 if the fused tcgen05 kernel can run these dims (dtype bf16, supported C/D/P/S), else 0 */
+/* 1 if a tensor-core path (fused or tiled, per dims.path) can run these dims, else 0 (generic CUDA-core path only) */
 int pasn_tcgen05_supported(const pasn_dims* dims);
 
 /* scratch needed by pasn_head_forward / pasn_occurrence_only for these dims */
 size_t pasn_head_workspace_bytes(const pasn_dims* dims);
 
-/* size of / fill the derived bf16 weight cache the tcgen05 path streams (never saved in checkpoints) */
+/* size of / fill the derived bf16 weight cache of the tensor-core path that serves these dims (fused: stage images in
+ * shared-memory byte order; tiled: row-major bf16 planes); depends on dims.dtype and dims.path; never saved in checkpoints */
 size_t pasn_packed_weights_bytes(const pasn_dims* dims);
 int pasn_pack_weights(const pasn_weights* w, const pasn_dims* dims, void* packed, void* stream);
 
 /* Replaces Video_XProtoNet.forward / push_forward minus the backbone
  * (src/models/Video_XProtoNet.py:82-98, :111-130; src/models/XProtoNet.py:51-67, :87-106).
  *   feat               [N,C,S] or [N,S,C] (dims.layout), dims.dtype
- *   packed             result of pasn_pack_weights, or NULL (then only the generic path can run)
+ *   packed             result of pasn_pack_weights for the same dims, or NULL (then only the generic path can run)
  *   logits             [N,K] fp32
  *   similarity         [N,P] fp32           ((cos+1)/2)
  *   occurrence_map     [N,P,S] dims.dtype, or NULL to skip the store
@@ -132,9 +135,12 @@ int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packe
                       float* distance, const pasn_push_args* push, void* workspace, size_t workspace_bytes,
                       void* stream);
 
-/* Replaces Video_XProtoNet.compute_occurence_map minus the backbone (src/models/Video_XProtoNet.py:100-109). */
-int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dims* dims, void* occurrence_map,
-                         void* workspace, size_t workspace_bytes, void* stream);
+/* Replaces Video_XProtoNet.compute_occurence_map minus the backbone (src/models/Video_XProtoNet.py:100-109; called once
+ * more per training step by TransformLoss, src/loss/loss.py:302).  Runs the occurrence branch alone: on the tiled
+ * tensor-core path when dims.path = PASN_PATH_TILED (`packed` = pasn_pack_weights with the same dims), on the generic
+ * CUDA-core path otherwise (`packed` ignored). */
+int pasn_occurrence_only(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
+                         void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the head (training: loss.backward() through Video_XProtoNet.forward, src/agents/XProtoNet_Base.py:397,
  * src/agents/Video_XProtoNet_e2e.py:138).  fp32 CUDA-core path; forward intermediates are recomputed, nothing has

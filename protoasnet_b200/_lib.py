@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libpasn_b200.so")
 PASN_F32, PASN_BF16 = 0, 1
 PASN_LAYOUT_NCS, PASN_LAYOUT_NSC = 0, 1
 PASN_OCC_ABS = 0
-PASN_PATH_AUTO, PASN_PATH_GENERIC, PASN_PATH_TCGEN05 = 0, 1, 2
+PASN_PATH_AUTO, PASN_PATH_GENERIC, PASN_PATH_TCGEN05, PASN_PATH_TILED = 0, 1, 2, 3
 
 # every symbol include/pasn.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
@@ -80,7 +80,7 @@ def load() -> C.CDLL:
     lib.pasn_head_forward.argtypes = [vp, C.POINTER(PasnWeights), vp, C.POINTER(PasnDims), vp, vp, vp, vp, vp,
                                       C.POINTER(PasnPushArgs), vp, sz, vp]
     lib.pasn_occurrence_only.restype = C.c_int
-    lib.pasn_occurrence_only.argtypes = [vp, C.POINTER(PasnWeights), C.POINTER(PasnDims), vp, vp, sz, vp]
+    lib.pasn_occurrence_only.argtypes = [vp, C.POINTER(PasnWeights), vp, C.POINTER(PasnDims), vp, vp, sz, vp]
     lib.pasn_push_init.restype = C.c_int
     lib.pasn_push_init.argtypes = [vp, i32, vp]
     lib.pasn_push_decode.restype = C.c_int

@@ -10,16 +10,30 @@ static bool dims_ok(const pasn_dims* d) {
   if (d->dtype != PASN_F32 && d->dtype != PASN_BF16) return false;
   if (d->layout != PASN_LAYOUT_NCS && d->layout != PASN_LAYOUT_NSC) return false;
   if (d->occ_act != PASN_OCC_ABS) return false;
-  if (d->path < PASN_PATH_AUTO || d->path > PASN_PATH_TCGEN05) return false;
+  if (d->path < PASN_PATH_AUTO || d->path > PASN_PATH_TILED) return false;
   return true;
 }
 
-static bool use_tcgen05(const pasn_dims& d, const void* packed, int* err) {
+// which kernel family serves these dims: 0 generic, 1 fused token kernel, 2 tiled GEMM chain; *err when an explicitly
+// requested family cannot run them
+enum { FAM_GENERIC = 0, FAM_FUSED = 1, FAM_TILED = 2 };
+static int resolve_family(const pasn_dims& d, int* err) {
   *err = PASN_OK;
-  if (d.path == PASN_PATH_GENERIC) return false;
-  bool ok = sm100_supported(d) && packed != nullptr;
-  if (d.path == PASN_PATH_TCGEN05 && !ok) *err = PASN_ERR_UNSUPPORTED;
-  return ok;
+  switch (d.path) {
+    case PASN_PATH_GENERIC: return FAM_GENERIC;
+    case PASN_PATH_TCGEN05:
+      if (sm100_supported(d)) return FAM_FUSED;
+      *err = PASN_ERR_UNSUPPORTED;
+      return FAM_GENERIC;
+    case PASN_PATH_TILED:
+      if (tiled_supported(d)) return FAM_TILED;
+      *err = PASN_ERR_UNSUPPORTED;
+      return FAM_GENERIC;
+    default:
+      if (sm100_supported(d)) return FAM_FUSED;
+      if (tiled_supported(d)) return FAM_TILED;
+      return FAM_GENERIC;
+  }
 }
 
 // ---- measurement hooks ------------------------------------------------------------------------
@@ -104,27 +118,38 @@ extern "C" const char* pasn_strerror(int status) {
 
 extern "C" int pasn_tcgen05_supported(const pasn_dims* dims) {
   if (!dims_ok(dims)) return 0;
-  return sm100_supported(*dims) ? 1 : 0;
+  int err;
+  return resolve_family(*dims, &err) != FAM_GENERIC ? 1 : 0;
 }
 
 extern "C" size_t pasn_head_workspace_bytes(const pasn_dims* dims) {
   if (!dims_ok(dims)) return 0;
-  size_t g = generic_workspace_bytes(*dims);
-  size_t t = (dims->path != PASN_PATH_GENERIC && sm100_supported(*dims)) ? sm100_workspace_bytes(*dims) : 0;
-  if (dims->path == PASN_PATH_TCGEN05) return t;
-  if (dims->path == PASN_PATH_GENERIC) return g;
-  return g > t ? g : t;
+  int err;
+  const int fam = resolve_family(*dims, &err);
+  size_t need = generic_workspace_bytes(*dims);   // the generic path stays available as the NULL-`packed` fallback
+  if (dims->path == PASN_PATH_TCGEN05 || dims->path == PASN_PATH_TILED) need = 0;
+  if (fam == FAM_FUSED) { const size_t t = sm100_workspace_bytes(*dims); need = t > need ? t : need; }
+  if (fam == FAM_TILED || (dims->path == PASN_PATH_AUTO && tiled_supported(*dims))) {   // AUTO: occurrence-only may run tiled
+    const size_t t = tiled_workspace_bytes(*dims);
+    need = t > need ? t : need;
+  }
+  return need;
 }
 
 extern "C" size_t pasn_packed_weights_bytes(const pasn_dims* dims) {
-  if (!dims_ok(dims) || !sm100_supported(*dims)) return 0;
-  return sm100_packed_bytes(*dims);
+  if (!dims_ok(dims)) return 0;
+  int err;
+  const int fam = resolve_family(*dims, &err);
+  return fam == FAM_FUSED ? sm100_packed_bytes(*dims) : (fam == FAM_TILED ? tiled_packed_bytes(*dims) : 0);
 }
 
 extern "C" int pasn_pack_weights(const pasn_weights* w, const pasn_dims* dims, void* packed, void* stream) {
   if (!w || !dims_ok(dims) || !packed) return PASN_ERR_INVALID;
-  if (!sm100_supported(*dims)) return PASN_ERR_UNSUPPORTED;
-  return sm100_pack_weights(*w, *dims, packed, (cudaStream_t)stream);
+  int err;
+  const int fam = resolve_family(*dims, &err);
+  if (fam == FAM_FUSED) return sm100_pack_weights(*w, *dims, packed, (cudaStream_t)stream);
+  if (fam == FAM_TILED) return tiled_pack_weights(*w, *dims, packed, (cudaStream_t)stream);
+  return PASN_ERR_UNSUPPORTED;
 }
 
 extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
@@ -137,19 +162,29 @@ extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const 
   if (push && (!push->labels || !push->proto_class || !push->best_key)) return PASN_ERR_INVALID;   // best_vec is optional
   if (push && (push->global_offset < 0 || push->global_offset + dims->N > 0xFFFFFFFFll)) return PASN_ERR_INVALID;
   int err;
-  if (use_tcgen05(*dims, packed, &err))
+  int fam = resolve_family(*dims, &err);
+  if (err) return err;
+  if (fam != FAM_GENERIC && packed == nullptr) {
+    if (dims->path != PASN_PATH_AUTO) return PASN_ERR_UNSUPPORTED;
+    fam = FAM_GENERIC;
+  }
+  if (fam == FAM_FUSED)
     return sm100_head_forward(feat, *w, packed, *dims, logits, similarity, occurrence_map, features_extracted,
                               distance, push, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (err) return err;
+  if (fam == FAM_TILED)
+    return tiled_head_forward(feat, *w, packed, *dims, logits, similarity, occurrence_map, features_extracted, distance,
+                              push, workspace, workspace_bytes, (cudaStream_t)stream);
   return generic_head_forward(feat, *w, *dims, logits, similarity, occurrence_map, features_extracted, distance, push,
                               workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int pasn_occurrence_only(const void* feat, const pasn_weights* w, const pasn_dims* dims,
+extern "C" int pasn_occurrence_only(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
                                     void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dims_ok(dims) || !w || !occurrence_map) return PASN_ERR_INVALID;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
-  pasn_dims d = *dims;
-  return generic_occurrence_only(feat, *w, d, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (dims->path == PASN_PATH_TILED && !(tiled_supported(*dims) && packed)) return PASN_ERR_UNSUPPORTED;
+  if (dims->path == PASN_PATH_TILED)
+    return tiled_occurrence_only(feat, *w, packed, *dims, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
+  return generic_occurrence_only(feat, *w, *dims, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
 }

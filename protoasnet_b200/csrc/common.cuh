@@ -85,6 +85,17 @@ int launch_proto_stage(const float* feats /*[N,P,D]*/, const float* protos, cons
                        int D, int K, float* logits, float* sim, float* dist, const pasn_push_args* push,
                        cudaStream_t st);
 
+// ---- tiled tcgen05 path (tiled.cu, tc_gemm.cu): chain of TMA-fed GEMMs, bf16 or fp32 (hi/lo split) -----------------
+bool tiled_supported(const pasn_dims& d);
+size_t tiled_workspace_bytes(const pasn_dims& d);
+size_t tiled_packed_bytes(const pasn_dims& d);
+int tiled_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, cudaStream_t st);
+int tiled_head_forward(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, float* logits,
+                       float* sim, void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+int tiled_occurrence_only(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, void* occ, void* ws,
+                          size_t ws_bytes, cudaStream_t st);
+
 // ---- fused tcgen05 path (head_sm100.cu) -----------------------------------------------------
 bool sm100_supported(const pasn_dims& d);
 size_t sm100_workspace_bytes(const pasn_dims& d);

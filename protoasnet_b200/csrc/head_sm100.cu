@@ -63,7 +63,7 @@ __device__ __forceinline__ long long gtimer_ns() {
   return t;
 }
 }  // namespace
-#define K2_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0 && (slot) < 240) p.trace[768 + 16 + (slot)] = gtimer_ns(); } while (0)
+#define K2_TRACE(slot) do { if (p.trace != nullptr && blockIdx.x == 0 && (slot) < 184) p.trace[768 + 16 + (slot)] = gtimer_ns(); } while (0)
 
 __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
           if (!ok) break;
           fence_proxy_async_all();
         }
+        K2_TRACE(16 + it * 8 + 7);
+        if (p.trace != nullptr && blockIdx.x == 0 && it < 32) p.trace[768 + 200 + it] = tile;
         for (int kc = 0; kc < 4; ++kc, ++u) {
           const uint32_t s = u & 1, ph = (u >> 1) & 1;
           if (!(ok = bwait(&bars[2 + s], ph ^ 1, ctx, 611))) break;

@@ -220,11 +220,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     };
     auto store_direct = [&](const Output& o, const float (&v)[64], int col0, int row, int b, bool row_ok) {
       if (!row_ok) return;
+      const int ncols = o.ncols ? o.ncols : g.N;
       const long long base = (long long)b * o.bs + (long long)row * o.ld;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const int col = col0 + j;
-        if (col >= g.N) continue;
+        if (col >= ncols) continue;
         if (o.mode == OUT_F32) {
           reinterpret_cast<float*>(o.ptr)[base + col] = v[j];
         } else {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           v[4 * j4 + 3] = act_apply(fmaf(rowterm, cc.w, v[4 * j4 + 3] + bb.w), g.act);
         }
         if (g.psum != nullptr) {
-          const bool rounded = g.out[0].mode == OUT_BF16;
+          const bool rounded = g.psum_rounded != 0;
 #pragma unroll
           for (int j = 0; j < 64; ++j) psum += (col0 + j < g.N) ? (rounded ? round_bf16(v[j]) : v[j]) : 0.f;
         }
@@ -372,12 +373,12 @@ int launch(const Gemm& g, cudaStream_t st) {
                 g.a_batched ? g.batch : 1, (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, BK, BM))
     return PASN_ERR_ALIGN;
   if (!g.b_mn_major) {
-    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb, (unsigned long long)g.N,
-                  g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)g.bn))
+    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)g.bn))
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
-    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb, (unsigned long long)g.K,
-                  g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
+    if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.K), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
       return PASN_ERR_ALIGN;
   }
   for (int mi = 0; mi < 2; ++mi) {
@@ -389,11 +390,12 @@ int launch(const Gemm& g, cudaStream_t st) {
     const bool f32 = o.mode == OUT_F32;
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int elt = f32 ? 4 : 2;
-    bool okm = make_map(&kp.tmO[2 * mi], dt, elt, o.ptr, (unsigned long long)g.N, (unsigned long long)g.M, g.batch,
+    const unsigned long long ncols = o.ncols ? o.ncols : g.N;
+    bool okm = make_map(&kp.tmO[2 * mi], dt, elt, o.ptr, ncols, (unsigned long long)g.M, g.batch,
                         (unsigned long long)o.ld * elt, (unsigned long long)o.bs * elt, f32 ? 32 : 64, 32);
     if (okm && o.mode == OUT_BF16_HILO)
       okm = make_map(&kp.tmO[2 * mi + 1], dt, elt, reinterpret_cast<const char*>(o.ptr) + (size_t)o.lo_off * 2,
-                     (unsigned long long)g.N, (unsigned long long)g.M, g.batch, (unsigned long long)o.ld * elt,
+                     ncols, (unsigned long long)g.M, g.batch, (unsigned long long)o.ld * elt,
                      (unsigned long long)o.bs * elt, 64, 32);
     kp.out_tma[mi] = okm ? 1 : 0;
   }

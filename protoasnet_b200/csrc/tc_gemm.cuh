@@ -20,6 +20,7 @@ struct Output {
   int mode;           // OUT_*
   long long ld, bs;   // row / batch stride in elements
   int lo_off;         // OUT_BF16_HILO: column offset of the lo half (the hi half starts at column 0)
+  int ncols;          // columns of this output (0: N); columns beyond it are computed but not stored
 };
 
 struct Gemm {
@@ -27,6 +28,7 @@ struct Gemm {
   const void* A; long long lda, a_bs; int a_batched; int ka;
   // B: K-major [b_batched ? batch : 1][N][kb] (row stride ldb) or, b_mn_major, [batch?][K][nb] with n contiguous
   const void* B; long long ldb, b_bs; int b_batched; int kb; int b_mn_major;
+  int b_rows;                    // rows B really has per batch item (0: N, or K when b_mn_major); rows beyond read as zero
   int M, N, K, batch;            // K per pass
   int npass; int a_off[3], b_off[3];
   int bn;                        // tile width: 64, 128 or 256
@@ -34,7 +36,8 @@ struct Gemm {
   const float* rowparts; int nparts; const float* colvec;   // rank-1 term (sum_t rowparts[(b*M+m)*nparts + t]) * colvec[n], or null
   int act;
   Output out[2];
-  float* psum;                   // optional [batch*M][tiles_n]: per-tile row sums of the values written to out[0] (after rounding)
+  float* psum;                   // optional [batch*M][2*tiles_n]: row sums of the outputs per column half-tile ...
+  int psum_rounded;              // ... of the bf16-rounded values (what a bf16 consumer of out[0] will read) or of the fp32 values
 };
 
 int launch(const Gemm& g, cudaStream_t st);   // 0 or a negative pasn_status

@@ -44,8 +44,7 @@ class _HeadRuntime:
     def __init__(self, owner: "PrototypeHeadMixin"):
         self.owner = owner
         self._ws: Optional[torch.Tensor] = None
-        self._packed: Optional[torch.Tensor] = None
-        self._packed_key = None
+        self._packed: Dict = {}
 
     def _weights_struct(self, m) -> Tuple[PasnWeights, list]:
         a, o = m.add_on_layers, m.occurrence_module
@@ -64,15 +63,20 @@ class _HeadRuntime:
         return self._ws
 
     def _packed_weights(self, lib, dims: PasnDims, w: PasnWeights, tensors, device, stream) -> Optional[torch.Tensor]:
+        """Derived bf16 weight cache of the tensor-core path that serves ``dims`` (fused stage images or tiled planes),
+        one entry per (shape, dtype, path); re-packed when a parameter's version counter or storage changes."""
         if not lib.pasn_tcgen05_supported(C.byref(dims)):
             return None
-        key = (str(device), dims.C, dims.D, dims.P, tuple((t.data_ptr(), t._version) for t in tensors[:9]))
-        if self._packed is None or self._packed_key != key:
+        slot = (str(device), dims.C, dims.D, dims.P, dims.dtype, dims.path)
+        key = tuple((t.data_ptr(), t._version) for t in tensors[:9])
+        ent = self._packed.get(slot)
+        if ent is None or ent[0] != key:
             nbytes = int(lib.pasn_packed_weights_bytes(C.byref(dims)))
-            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            _lib.check(lib.pasn_pack_weights(C.byref(w), C.byref(dims), self._packed.data_ptr(), stream), "pasn_pack_weights")
-            self._packed_key = key
-        return self._packed
+            buf = ent[1] if ent is not None and ent[1].numel() == nbytes else torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.pasn_pack_weights(C.byref(w), C.byref(dims), buf.data_ptr(), stream), "pasn_pack_weights")
+            self._packed[slot] = (key, buf)
+            ent = self._packed[slot]
+        return ent[1]
 
     def make_dims(self, x: torch.Tensor, path: int) -> Tuple[PasnDims, torch.Tensor, Tuple[int, ...]]:
         m = self.owner
@@ -139,17 +143,22 @@ class _HeadRuntime:
         return {"logits": logits, "similarity": sim, "occurrence_map": occ, "features_extracted": feats, "distance": dist}
 
     def occurrence_only(self, x: torch.Tensor) -> torch.Tensor:
+        """compute_occurence_map: the occurrence branch alone, on the tiled tensor-core path when the shape qualifies."""
         lib = _lib.load()
         m = self.owner
-        dims, x, spatial = self.make_dims(x, _lib.PASN_PATH_GENERIC)
+        path = m.kernel_path if m.kernel_path == _lib.PASN_PATH_GENERIC else _lib.PASN_PATH_TILED
+        dims, x, spatial = self.make_dims(x, path)
+        if path == _lib.PASN_PATH_TILED and not lib.pasn_tcgen05_supported(C.byref(dims)):
+            dims.path = _lib.PASN_PATH_GENERIC
         dev = x.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            w, _ = self._weights_struct(m)
+            w, tensors = self._weights_struct(m)
             occ = torch.empty((dims.N, dims.P, 1) + spatial, dtype=x.dtype, device=dev)
             if dims.N > 0:
+                packed = self._packed_weights(lib, dims, w, tensors, dev, stream) if dims.path == _lib.PASN_PATH_TILED else None
                 ws = self._workspace(lib, dims, dev)
-                _lib.check(lib.pasn_occurrence_only(x.data_ptr(), C.byref(w), C.byref(dims), occ.data_ptr(),
+                _lib.check(lib.pasn_occurrence_only(x.data_ptr(), C.byref(w), _ptr(packed), C.byref(dims), occ.data_ptr(),
                                                     ws.data_ptr(), ws.numel(), stream), "pasn_occurrence_only")
         return occ
 

@@ -24,8 +24,8 @@ g = t[16:]
 print(f"K1 CTA0: start 0, end {k1e - k1s} ns")
 rel = lambda v: (v - k1s) if v else None
 print(f"K2 CTA0: start {rel(g[0])}, prologue done {rel(g[1])}, griddep_wait passed {rel(g[2])}, end {rel(g[3])}")
-for it in range(4):
+for it in range(20):
     b = g[16 + it * 8: 16 + it * 8 + 8]
     if not b[0]:
         break
-    print(f"  tile {it}: stage full seen {[rel(v) for v in b[:4]]}, MMAs committed {rel(b[4])}, epilogue start {rel(b[5])}, end {rel(b[6])}")
+    print(f"  it {it} tile {t[200 + it]}: ready-wait passed {rel(b[7])}, stage full seen {[rel(v) for v in b[:4]]}, MMAs committed {rel(b[4])}, epilogue start {rel(b[5])}, end {rel(b[6])}")
