@@ -138,12 +138,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       const uint64_t pol_first = l2_policy_evict_first();
       uint32_t u = 0;
       bool ok = true;
+      int dbg_grabs = 0;
       for (int it = 0; ok; ++it) {
         int tile = -1;
         if (dynamic) {
           const int nslots = p.grid1 * p.cpc;
           for (;;) {
             const int i = atomicAdd(p.queue, 1);
+            if (p.trace != nullptr && blockIdx.x == 0 && dbg_grabs < 4) {   // first grabs: (time, slot)
+              p.trace[768 + 240 + 2 * dbg_grabs] = gtimer_ns();
+              p.trace[768 + 240 + 2 * dbg_grabs + 1] = i;
+              ++dbg_grabs;
+            }
             if (i >= nslots) break;
             const int rnd = i / p.grid1, clip = (i - rnd * p.grid1) * p.cpc + rnd;
             if (clip >= p.N) continue;
