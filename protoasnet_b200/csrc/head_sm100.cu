@@ -40,7 +40,9 @@ constexpr uint32_t K2_STAGE = 65536;                 // A_hi chunk 16 KB | A_lo 
 constexpr uint32_t K2_SM_V = 2 * K2_STAGE;           // prototypes fp32 [P][257]
 constexpr uint32_t K2_V_BYTES = PP_MAX * 257 * 4;    // 49344
 constexpr uint32_t K2_SM_MISC = K2_SM_V + 49408;     // 180480
-constexpr uint32_t K2_SMEM = K2_SM_MISC + 8192;
+constexpr uint32_t K2_SM_ORD = K2_SM_MISC + 8192;     // uint16 tile order table (dynamic hand-out), K2_MAX_ORD entries
+constexpr int K2_MAX_ORD = 4096;
+constexpr uint32_t K2_SMEM = K2_SM_ORD + 2 * K2_MAX_ORD;
 
 struct K2Params {
   const uint8_t* feimg; const float* osum; const uint8_t* packed; size_t off_w2, off_b2;
@@ -127,7 +129,43 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   // while stragglers of the token kernel are still running thus works on finished tiles, and late CTAs take fewer.
   // Without it (PASN_K2_EARLY=0) the tiles are dealt round-robin after the whole token kernel has completed.
   // The loader publishes each tile index (or -1) in a 4-slot ring guarded by mbarriers; MMA issuer and epilogue follow.
-  const bool dynamic = p.ready != nullptr;
+  const bool dynamic = p.ready != nullptr && p.ntiles <= K2_MAX_ORD;
+  uint16_t* s_ord = reinterpret_cast<uint16_t*>(smem + K2_SM_ORD);
+  if (dynamic) {
+    // order table: walk the slots (round-major), keep the slot of each tile's latest clip.  Every CTA builds the same
+    // table: contiguous slot range per thread, count, block-wide exclusive scan, fill.
+    int* s_cnt = reinterpret_cast<int*>(smem);   // the stage ring is not in use yet
+    const int nslots = p.grid1 * p.cpc;
+    const int per = (nslots + K2_THREADS - 1) / K2_THREADS;
+    auto emit_tile = [&](int i) -> int {   // tile handed out at slot i, or -1
+      const int rnd = i / p.grid1, clip = (i - rnd * p.grid1) * p.cpc + rnd;
+      if (clip >= p.N) return -1;
+      const int t = clip / p.cpt, c0 = t * p.cpt;
+      int c1 = c0 + p.cpt;
+      if (c1 > p.N) c1 = p.N;
+      int key = 0;
+      for (int c = c0; c < c1; ++c) key = max(key, c % p.cpc);
+      int first = c0;
+      while (first % p.cpc != key) ++first;
+      return clip == first ? t : -1;
+    };
+    const int i0 = tid * per, i1 = min(nslots, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += emit_tile(i) >= 0 ? 1 : 0;
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int j = 0; j < K2_THREADS; ++j) { const int c = s_cnt[j]; s_cnt[j] = run; run += c; }
+    }
+    __syncthreads();
+    int pos = s_cnt[tid];
+    for (int i = i0; i < i1; ++i) {
+      const int t = emit_tile(i);
+      if (t >= 0) s_ord[pos++] = (uint16_t)t;
+    }
+    __syncthreads();
+  }
   if (tid == 0) K2_TRACE(1);   // prologue done
 
   if (warp == 9) {
@@ -142,26 +180,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
       for (int it = 0; ok; ++it) {
         int tile = -1;
         if (dynamic) {
-          const int nslots = p.grid1 * p.cpc;
-          for (;;) {
-            const int i = atomicAdd(p.queue, 1);
-            if (p.trace != nullptr && blockIdx.x == 0 && dbg_grabs < 4) {   // first grabs: (time, slot)
-              p.trace[768 + 240 + 2 * dbg_grabs] = gtimer_ns();
-              p.trace[768 + 240 + 2 * dbg_grabs + 1] = i;
-              ++dbg_grabs;
-            }
-            if (i >= nslots) break;
-            const int rnd = i / p.grid1, clip = (i - rnd * p.grid1) * p.cpc + rnd;
-            if (clip >= p.N) continue;
-            const int t = clip / p.cpt, c0 = t * p.cpt;
-            int c1 = c0 + p.cpt;
-            if (c1 > p.N) c1 = p.N;
-            int key = 0;
-            for (int c = c0; c < c1; ++c) key = max(key, c % p.cpc);
-            int first = c0;
-            while (first % p.cpc != key) ++first;
-            if (clip == first) { tile = t; break; }
+          const int e = atomicAdd(p.queue, 1);
+          if (p.trace != nullptr && blockIdx.x == 0 && dbg_grabs < 4) {   // first grabs: (time, queue position)
+            p.trace[768 + 240 + 2 * dbg_grabs] = gtimer_ns();
+            p.trace[768 + 240 + 2 * dbg_grabs + 1] = e;
+            ++dbg_grabs;
           }
+          tile = e < p.ntiles ? (int)s_ord[e] : -1;
         } else {
           tile = (int)blockIdx.x + it * (int)gridDim.x;
           if (tile >= p.ntiles) tile = -1;

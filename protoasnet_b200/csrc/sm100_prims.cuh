@@ -187,6 +187,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          | ((a_mn_major & 1u) << 15) | ((b_mn_major & 1u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// kind::f16 with per-operand element type (F16 = 0, BF16 = 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_bf16, uint32_t b_bf16, uint32_t a_mn_major,
+                                                     uint32_t b_mn_major) {
+  return (1u << 4) | ((a_bf16 & 1u) << 7) | ((b_bf16 & 1u) << 10) | ((a_mn_major & 1u) << 15) | ((b_mn_major & 1u) << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05.mma / commit
 // ----------------------------------------------------------------------------------------------
@@ -354,6 +361,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// pack two fp32 -> f16x2 (lo = first / even element)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 

@@ -11,6 +11,7 @@
 //
 // Every mbarrier wait is bounded: a protocol fault becomes an error code in *err, not a hung GPU.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "sm100_prims.cuh"
 #include "tc_gemm.cuh"
@@ -105,7 +106,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   const int bn = g.bn;
   const int tiles_per_batch = kp.tiles_m * kp.tiles_n;
   const int ntiles = g.batch * tiles_per_batch;
-  const int nk = g.npass * kp.nkb;   // k-blocks per tile
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)bn, 0, g.b_mn_major ? 1u : 0u);
+      uint32_t idesc[4];
+      for (int q = 0; q < 4; ++q)
+        idesc[q] = make_idesc_16(BM, (uint32_t)bn, g.a_f16[q] ? 0u : 1u, g.b_f16[q] ? 0u : 1u, 0, g.b_mn_major ? 1u : 0u);
       constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
       const uint32_t b_lbo = g.b_mn_major ? 8192u : 16u, b_kstep = g.b_mn_major ? 128u : 2u;
       const uint32_t bar0 = smem_u32(bars);
@@ -150,16 +152,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         if (!(ok = bwait(&bars[B_ACCEMPTY + buf], ((i >> 1) & 1) ^ 1, kp.err, 711))) break;
         tc_fence_after();
         const uint32_t d = tbase + 256u * buf;
-        for (int kk = 0; kk < nk; ++kk) {
-          if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
-          tc_fence_after();
-          const uint32_t sa = sbase + s * STAGE_BYTES;
-          const uint32_t alo = desc_lo(sa, 16), blo = desc_lo(sa + A_BYTES, b_lbo);
+        for (int pass = 0; pass < g.npass && ok; ++pass) {
+          const uint32_t id = idesc[pass];
+          for (int kb = 0; kb < kp.nkb; ++kb) {
+            if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
+            tc_fence_after();
+            const uint32_t sa = sbase + s * STAGE_BYTES;
+            const uint32_t alo = desc_lo(sa, 16), blo = desc_lo(sa + A_BYTES, b_lbo);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * 2, HI, blo + k4 * b_kstep, HI, idesc, (kk | k4) ? 1u : 0u);
-          mma_commit_a(bar0 + 8u * (B_EMPTY + s));
-          s = s + 1 == STAGES ? 0 : s + 1;
-          ph ^= (s == 0) ? 1u : 0u;
+            for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * 2, HI, blo + k4 * b_kstep, HI, id, (pass | kb | k4) ? 1u : 0u);
+            mma_commit_a(bar0 + 8u * (B_EMPTY + s));
+            s = s + 1 == STAGES ? 0 : s + 1;
+            ph ^= (s == 0) ? 1u : 0u;
+          }
         }
         if (ok) mma_commit_a(bar0 + 8u * (B_ACCFULL + buf));
       }
@@ -170,8 +175,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t slab0 = sbase + SM_STG + (uint32_t)w * 2u * SLAB_BYTES;
     float* vecs = reinterpret_cast<float*>(smem + SM_VEC + w * 512);   // [0,64) bias slice, [64,128) colvec slice
-    const int half_cols = bn / 2;
-    const int ngroups = (half_cols + 63) / 64;
+    const int nh = bn >= 128 ? 2 : 1;            // column halves in use (a 64-wide tile is one 64-column group: half 0 only)
+    const int half_cols = bn / nh;
+    const int ngroups = half_cols / 64;
     uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
     bool ok = true;
     int i = 0;
@@ -199,9 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
-              if (o.mode == OUT_BF16_HILO && bx == 1) { a0 -= round_bf16(a0); a1 -= round_bf16(a1); }
-              pk[j] = pack_bf16x2(a0, a1);
+              const float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
+              pk[j] = (o.mode == OUT_BF16_HILO && bx == 1) ? pack_f16x2(a0 - round_bf16(a0), a1 - round_bf16(a1)) : pack_bf16x2(a0, a1);
             }
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -232,7 +237,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
           const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
           p16[base + col] = hi;
-          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+          if (o.mode == OUT_BF16_HILO)
+            reinterpret_cast<__half*>(o.ptr)[base + o.lo_off + col] = __float2half_rn(v[j] - __bfloat162float(hi));
         }
       }
     };
@@ -252,6 +258,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       float psum = 0.f;
       if (!(ok = bwait(&bars[B_ACCFULL + buf], (i >> 1) & 1, kp.err, 721))) break;
       tc_fence_after();
+      if (h >= nh) {   // nothing to read for this warp: release the accumulator, keep the psum table dense
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+        if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = 0.f;
+        continue;
+      }
       for (int cg = 0; cg < ngroups; ++cg) {
         const int cl = h * half_cols + 64 * cg;       // column inside the tile
         const int col0 = n0 + cl;
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         {
           uint32_t ra[32], rb[32];
           tmem_ld_x32(tl + 256u * buf + (uint32_t)cl, ra);
-          if (half_cols - 64 * cg > 32) tmem_ld_x32(tl + 256u * buf + (uint32_t)cl + 32u, rb);
+          tmem_ld_x32(tl + 256u * buf + (uint32_t)cl + 32u, rb);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(ra[j]); v[32 + j] = __uint_as_float(rb[j]); }
@@ -353,7 +365,7 @@ bool available() { return encode_fn() != nullptr; }
 
 int launch(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;
-  if (g.npass < 1 || g.npass > 3 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
+  if (g.npass < 1 || g.npass > 4 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
   static int* d_err = nullptr;
   static bool attr_done = false;
   if (!attr_done) {

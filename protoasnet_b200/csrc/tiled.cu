@@ -12,6 +12,8 @@
 //   FE = pooled W2^T + (sum_s O[p,s]) b2     W2 applied after pooling (exact in real arithmetic)
 //   cosine / (.+1)/2 / logits / 1-s / push keys: proto_stage.cu (fp32)
 // Hidden activations are bf16 in HBM between the GEMMs (hi|lo planes in fp32 mode).
+#include <cuda_fp16.h>
+
 #include "tc_gemm.cuh"
 
 namespace pasn {
@@ -76,7 +78,7 @@ PackLayout pack_layout(const pasn_dims& d) {
   return L;
 }
 
-// fp32 [rows][cols] -> bf16 planes [rows][ex*cols]: plane 0 = round(w), plane 1 = round(w - plane 0)
+// fp32 [rows][cols] -> 16-bit planes [rows][ex*cols]: plane 0 = bf16(w), plane 1 = fp16(w - plane 0)
 __global__ void pack_planes_kernel(const float* __restrict__ w, int rows, int cols, int ex, __nv_bfloat16* __restrict__ out) {
   const long long n = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -84,7 +86,7 @@ __global__ void pack_planes_kernel(const float* __restrict__ w, int rows, int co
     const float v = w[i];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     out[(size_t)r * ex * cols + c] = hi;
-    if (ex == 2) out[(size_t)r * ex * cols + cols + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (ex == 2) reinterpret_cast<__half*>(out)[(size_t)r * ex * cols + cols + c] = __float2half_rn(v - __bfloat162float(hi));
   }
 }
 __global__ void pack_bias_kernel(const float* __restrict__ b, int n, int round, float* __restrict__ out) {
@@ -111,7 +113,7 @@ __global__ void to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int 
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       __nv_bfloat16* row = out + ((size_t)n * S + s) * ex * C;
       row[c] = hi;
-      if (ex == 2) row[C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      if (ex == 2) reinterpret_cast<__half*>(row)[C + c] = __float2half_rn(v - __bfloat162float(hi));
     }
   }
 }
@@ -123,23 +125,18 @@ __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long 
     const float v = x[i];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     out[r * 2 * C + c] = hi;
-    out[r * 2 * C + C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    reinterpret_cast<__half*>(out)[r * 2 * C + C + c] = __float2half_rn(v - __bfloat162float(hi));
   }
 }
 
-void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo, bool a_is_weight) {
-  // product of an activation (planes at 0 / lo offset) and a weight; three passes: hi*hi, hi*lo(weight), lo(act)*hi
-  if (ex == 1) { g.npass = 1; g.a_off[0] = g.b_off[0] = 0; return; }
-  g.npass = 3;
-  if (!a_is_weight) {   // A = activation, B = weight
-    g.a_off[0] = 0; g.b_off[0] = 0;
-    g.a_off[1] = 0; g.b_off[1] = b_lo;
-    g.a_off[2] = a_lo; g.b_off[2] = 0;
-  } else {              // A = weight, B = activation
-    g.a_off[0] = 0; g.b_off[0] = 0;
-    g.a_off[1] = a_lo; g.b_off[1] = 0;
-    g.a_off[2] = 0; g.b_off[2] = b_lo;
-  }
+// passes of a product of two operands that each come as planes (hi bf16 at column 0, lo fp16 at column *_lo)
+void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo) {
+  for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = g.a_f16[q] = g.b_f16[q] = 0;
+  if (ex == 1) { g.npass = 1; return; }
+  g.npass = 4;                                   // hi*hi, hi*lo, lo*hi, lo*lo
+  g.b_off[1] = b_lo; g.b_f16[1] = 1;
+  g.a_off[2] = a_lo; g.a_f16[2] = 1;
+  g.a_off[3] = a_lo; g.a_f16[3] = 1; g.b_off[3] = b_lo; g.b_f16[3] = 1;
 }
 
 }  // namespace
@@ -230,7 +227,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.A = xt; g.lda = (long long)ex * C; g.a_bs = 0; g.a_batched = 0; g.ka = ex * C;
     g.B = occ_only ? W13 + (size_t)D * ex * C : W13; g.ldb = (long long)ex * C; g.b_bs = 0; g.b_batched = 0; g.kb = ex * C;
     g.M = (int)T; g.N = nA; g.K = C; g.batch = 1; g.bn = 256;
-    set_passes(g, ex, C, C, false);
+    set_passes(g, ex, C, C);
     g.bias = occ_only ? b13 + D : b13; g.act = tcg::ACT_RELU;
     g.out[0] = {Y, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_BF16_HILO, (long long)ex * nA, 0, nA};
     if ((rc = tcg::launch(g, st))) return rc;
@@ -242,7 +239,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.A = Y + g1_off; g.lda = (long long)ex * nA; g.a_batched = 0; g.ka = ex * nA - g1_off;
     g.B = W4; g.ldb = (long long)ex * D; g.b_batched = 0; g.kb = ex * D;
     g.M = (int)T; g.N = D2; g.K = D; g.batch = 1; g.bn = pick_bn(D2);
-    set_passes(g, ex, nA, D, false);
+    set_passes(g, ex, nA, D);
     g.bias = b4; g.act = tcg::ACT_RELU;
     g.out[0] = {G2, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_BF16_HILO, (long long)ex * D2, 0, D2};
     if ((rc = tcg::launch(g, st))) return rc;
@@ -258,7 +255,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.b_rows = S;   // tokens of this clip; the padded columns of the operand copy come out as exact zeros
     g.M = P; g.K = D2; g.batch = nb; g.bn = p.bn_c;
     g.N = ex == 2 ? p.Sp : S;
-    set_passes(g, ex, D2, D2, true);
+    set_passes(g, ex, D2, D2);
     g.act = tcg::ACT_ABS;
     int no = 0;
     const bool need_copy = !occ_only && !(p.occ_direct && occ_user != nullptr);
@@ -288,7 +285,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.B = Y; g.ldb = (long long)ex * 2 * D; g.b_bs = (long long)S * ex * 2 * D; g.b_batched = 1; g.kb = ex * 2 * D;
     g.b_mn_major = 1; g.b_rows = S;
     g.M = P; g.N = D; g.K = ex == 2 ? p.Sp : S; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
-    set_passes(g, ex, p.Sp, 2 * D, false);   // A = occurrence (activation planes), B = H1 (activation planes): hi*hi, hi*lo, lo*hi
+    set_passes(g, ex, p.Sp, 2 * D);
     g.act = tcg::ACT_NONE;
     g.out[0] = {POOL, tcg::OUT_BF16_HILO, (long long)2 * D, (long long)P * 2 * D, D};
     if ((rc = tcg::launch(g, st))) return rc;
@@ -299,8 +296,8 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.A = POOL; g.lda = 2 * D; g.a_batched = 0; g.ka = 2 * D;
     g.B = W2; g.ldb = (long long)ex * D; g.b_batched = 0; g.kb = ex * D;
     g.M = nb * P; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
-    if (ex == 1) { g.npass = 2; g.a_off[0] = 0; g.a_off[1] = D; g.b_off[0] = g.b_off[1] = 0; }
-    else set_passes(g, ex, D, D, false);
+    set_passes(g, ex, D, D);
+    if (ex == 1) { g.npass = 2; g.a_off[1] = D; g.a_f16[1] = 1; }   // pooled = bf16 hi + fp16 lo, W2 bf16
     g.rowparts = PSUM; g.nparts = 2 * p.tiles_n_c; g.colvec = b2;
     g.act = tcg::ACT_NONE;
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};
