@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "sm100_prims.cuh"
 #include "tc_gemm.cuh"
 
@@ -206,7 +208,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
-              pk[j] = (o.mode == OUT_BF16_HILO && bx == 1) ? pack_f16x2(a0 - round_bf16(a0), a1 - round_bf16(a1)) : pack_bf16x2(a0, a1);
+              if (o.mode == OUT_BF16_HILO && bx == 1) {
+                const float l0 = a0 - round_bf16(a0), l1 = a1 - round_bf16(a1);
+                pk[j] = g.lo_f16 ? pack_f16x2(l0, l1) : pack_bf16x2(l0, l1);
+              } else {
+                pk[j] = pack_bf16x2(a0, a1);
+              }
             }
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -237,8 +244,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
           const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
           p16[base + col] = hi;
-          if (o.mode == OUT_BF16_HILO)
-            reinterpret_cast<__half*>(o.ptr)[base + o.lo_off + col] = __float2half_rn(v[j] - __bfloat162float(hi));
+          if (o.mode == OUT_BF16_HILO) {
+            const float l = v[j] - __bfloat162float(hi);
+            if (g.lo_f16) reinterpret_cast<__half*>(o.ptr)[base + o.lo_off + col] = __float2half_rn(l);
+            else p16[base + o.lo_off + col] = __float2bfloat16_rn(l);
+          }
         }
       }
     };
@@ -362,6 +372,10 @@ bool out_aligned(const Output& o) {
 }  // namespace
 
 bool available() { return encode_fn() != nullptr; }
+bool lo_planes_f16() {
+  static const bool v = [] { const char* e = getenv("PASN_TILED_LO"); return !(e && e[0] == 'b'); }();
+  return v;
+}
 
 int launch(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;

@@ -38,10 +38,12 @@ struct Gemm {
   const float* rowparts; int nparts; const float* colvec;   // rank-1 term (sum_t rowparts[(b*M+m)*nparts + t]) * colvec[n], or null
   int act;
   Output out[2];
+  int lo_f16;                    // OUT_BF16_HILO writes its lo plane as fp16 (else bf16)
   float* psum;                   // optional [batch*M][2*tiles_n]: row sums of the outputs per column half-tile ...
   int psum_rounded;              // ... of the bf16-rounded values (what a bf16 consumer of out[0] will read) or of the fp32 values
 };
 
+bool lo_planes_f16();                         // lo planes are fp16 (default) or bf16 (PASN_TILED_LO=bf16)
 int launch(const Gemm& g, cudaStream_t st);   // 0 or a negative pasn_status
 bool available();                             // driver entry point for tensor-map encoding found
 

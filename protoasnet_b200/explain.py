@@ -82,12 +82,13 @@ def collect_model_products(model, dataloader, abstain_class: bool = True, keep_i
             prob = logits[:, : model.num_classes - 1].softmax(dim=1)
         else:
             prob = logits.softmax(dim=1)
+        occ32 = occ.float()      # on the main stream: every tensor the copy stream reads is complete at `done`
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(device))
         items = []
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
-            for t, sink in ((feats, feats_l), (dist, dist_l), (occ.float(), occ_l), (prob, pred_l)):
+            for t, sink in ((feats, feats_l), (dist, dist_l), (occ32, occ_l), (prob, pred_l)):
                 host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 host.copy_(t, non_blocking=True)
                 t.record_stream(copy_stream)

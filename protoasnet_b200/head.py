@@ -223,15 +223,22 @@ class HostPipeline:
     the batch instead of copy + compute.
 
         pipe = HostPipeline(model, chunks=4)
-        logits, sim = pipe(x_host_pinned)          # pinned host tensors, valid until the next call
+        logits, sim = pipe(x_host_pinned)          # pinned host tensors, complete on return, valid until the next call
+
+    Stream contract: the staging buffers are reused across calls, so the "kernels that read staging buffer i are done"
+    events persist from call to call (the next call's first copies wait for the previous call's last kernels).  With
+    ``sync=True`` (default) the call returns after the last device->host copy has completed; with ``sync=False`` it
+    returns immediately and ``pipe.done`` (a CUDA event) marks the point after which the host buffers may be read.
     """
 
-    def __init__(self, model, chunks: int = 4, device=None, want_occ: bool = False):
-        self.model, self.chunks, self.want_occ = model, max(1, int(chunks)), want_occ
+    def __init__(self, model, chunks: int = 4, device=None, want_occ: bool = False, sync: bool = True):
+        self.model, self.chunks, self.want_occ, self.sync = model, max(1, int(chunks)), want_occ, sync
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._stage = None
         self._host = None
+        self._free = [None, None]    # event per staging buffer: kernels that read it are done (persists across calls)
+        self.done = None
 
     @torch.no_grad()
     def __call__(self, x_host: torch.Tensor):
@@ -241,9 +248,13 @@ class HostPipeline:
         pieces = [(bounds[i], bounds[i + 1]) for i in range(self.chunks) if bounds[i + 1] > bounds[i]]
         cmax = max((b - a for a, b in pieces), default=0)
         key = (tuple(x_host.shape[1:]), x_host.dtype, cmax, n)
+        main = torch.cuda.current_stream(dev)
         if self._stage is None or self._stage[0] != key:
+            if self.done is not None:
+                self.done.synchronize()          # nothing may still be using the buffers we are about to replace
             bufs = [torch.empty((cmax,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=dev) for _ in range(2)]
             self._stage = (key, bufs)
+            self._free = [None, None]
             P, K = int(m.prototype_shape[0]), int(m.num_classes)
             host = {"logits": torch.empty((n, K), dtype=torch.float32).pin_memory(),
                     "similarity": torch.empty((n, P), dtype=torch.float32).pin_memory()}
@@ -251,8 +262,7 @@ class HostPipeline:
                 host["occurrence_map"] = torch.empty((n, P, 1) + tuple(x_host.shape[2:]), dtype=x_host.dtype).pin_memory()
             self._host = host
         bufs, host = self._stage[1], self._host
-        main = torch.cuda.current_stream(dev)
-        free = [None, None]      # event: kernels that read staging buffer i are done
+        free = self._free
         for i, (a, b) in enumerate(pieces):
             buf = bufs[i & 1][: b - a]
             with torch.cuda.stream(self.copy_stream):
@@ -270,6 +280,9 @@ class HostPipeline:
             done = torch.cuda.Event()
             done.record(main)
             free[i & 1] = done
+            self.done = done
+        if self.sync and self.done is not None:
+            self.done.synchronize()
         if self.want_occ:
             return host["logits"], host["similarity"], host["occurrence_map"]
         return host["logits"], host["similarity"]
@@ -486,10 +499,18 @@ def _video_backbone(base_architecture, pretrained, last_layer_num):
         raise RuntimeError("pretrained backbone weights need a download; pass pretrained=False and load a checkpoint")
     from torchvision.models.video import r2plus1d_18
 
-    class Resnet2p1dFeatures(nn.Sequential):
-        """torchvision r2plus1d_18 children[:last_layer_num] (reference: src/models/resnet_features.py:307-327)."""
+    class Resnet2p1dFeatures(nn.Module):
+        """torchvision r2plus1d_18 children[:last_layer_num] under ``.backbone`` -- the module layout (and hence the
+        checkpoint keys ``cnn_backbone.backbone.<i>...``) of the reference's wrapper, src/models/resnet_features.py:307-327."""
 
-    return Resnet2p1dFeatures(*list(r2plus1d_18(weights=None).children())[:last_layer_num])
+        def __init__(self):
+            super().__init__()
+            self.backbone = nn.Sequential(*list(r2plus1d_18(weights=None).children())[:last_layer_num])
+
+        def forward(self, x):
+            return self.backbone(x)
+
+    return Resnet2p1dFeatures()
 
 
 def _image_backbone(base_architecture, pretrained):
@@ -499,10 +520,22 @@ def _image_backbone(base_architecture, pretrained):
         raise RuntimeError("pretrained backbone weights need a download; pass pretrained=False and load a checkpoint")
     from torchvision.models import resnet18
 
-    class Resnet18Features(nn.Sequential):
-        """torchvision resnet18 without avgpool/fc -> [N,512,7,7] (reference: src/models/resnet_features.py:237-248)."""
+    class Resnet18Features(nn.Module):
+        """torchvision resnet18 without avgpool / fc -> [N,512,7,7], with the stem and the four stages as the named
+        attributes conv1 / bn1 / layer1..layer4, i.e. the checkpoint keys of the reference's ResNet_features
+        (src/models/resnet_features.py:126-214, :237-248)."""
 
-    return Resnet18Features(*list(resnet18(weights=None).children())[:-2])
+        def __init__(self):
+            super().__init__()
+            r = resnet18(weights=None)
+            self.conv1, self.bn1, self.relu, self.maxpool = r.conv1, r.bn1, r.relu, r.maxpool
+            self.layer1, self.layer2, self.layer3, self.layer4 = r.layer1, r.layer2, r.layer3, r.layer4
+
+        def forward(self, x):
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+            return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+    return Resnet18Features()
 
 
 def construct_Video_XProtoNet(base_architecture, pretrained=True, img_size=224, prototype_shape=(40, 256, 1, 1, 1),

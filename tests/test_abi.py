@@ -103,3 +103,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("name", ["video_resnet2p1d_18_last-3", "video_resnet2p1d_18_last-2", "image_resnet18"])
+def test_checkpoint_layout_matches_reference_models(name):
+    """state_dict keys and shapes of the models built from the reference's string backbones equal the reference's own
+    (tests/golden/state_dict_keys.json, generated by oracle/gen_golden_keys.py from the reference constructors): reference
+    checkpoints load with strict=True (src/agents/base.py:128, src/agents/XProtoNet_e2e.py:95)."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))[name]
+    if name.startswith("video"):
+        m = pasn.construct_Video_XProtoNet("resnet2p1d_18", pretrained=False, backbone_last_layer_num=int(name[-2:]))
+    else:
+        m = pasn.construct_XProtoNet("resnet18", pretrained=False, prototype_shape=(40, 512, 1, 1), num_classes=4)
+    own = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert own == ref
+    m.load_state_dict({k: torch.zeros(v) for k, v in ref.items()}, strict=True)
