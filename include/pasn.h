@@ -11,7 +11,11 @@
  *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all buffers
  *   - all calls are asynchronous on `stream`, never allocate, never synchronise, never throw
  *   - return value 0 on success, a negative pasn_status otherwise (pasn_strerror() explains it)
- *   - the library is stateless; one call sequence per stream at a time
+ *   - no per-call state is kept; process-wide state is limited to the measurement / debug hooks at the end of this
+ *     header and the sticky fault word (below); one call sequence per stream at a time
+ *   - every wait inside the tensor-core kernels is bounded.  A kernel that gives up writes a code into a host-mapped
+ *     fault word; from then on pasn_head_forward / pasn_occurrence_only / pasn_head_backward return PASN_ERR_FAULT
+ *     (no synchronisation needed to notice: the word lives in pinned host memory)
  *   - there is NO CPU implementation behind this ABI: without a CUDA device the compute calls fail
  */
 #ifndef PASN_H_
@@ -32,7 +36,10 @@ typedef enum {
   PASN_ERR_WORKSPACE = -2,   /* workspace too small                                   */
   PASN_ERR_CUDA = -3,        /* a CUDA runtime call or kernel launch failed           */
   PASN_ERR_UNSUPPORTED = -4, /* requested path (e.g. tcgen05) not available for dims  */
-  PASN_ERR_ALIGN = -5        /* pointer not aligned as required                       */
+  PASN_ERR_ALIGN = -5,       /* pointer not aligned as required                       */
+  PASN_ERR_FAULT = -6        /* an earlier kernel of this process hit a bounded-wait   */
+                             /* limit (internal pipeline fault): its results and      */
+                             /* everything computed since are invalid                 */
 } pasn_status;
 
 typedef enum { PASN_F32 = 0, PASN_BF16 = 1 } pasn_dtype;
@@ -199,6 +206,9 @@ int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_
 unsigned long long pasn_debug_launch_count(void);
 int pasn_debug_time_main_kernel(int enable);
 float pasn_debug_last_main_kernel_ms(void);
+/* sticky fault word (0 = none): read it / set it (tests) / clear it */
+int pasn_debug_fault(void);
+int pasn_debug_set_fault(int code);
 /* synchronises `stream` and returns the bounded-wait error code the fused tcgen05 kernels left in `workspace`
  * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid) */
 int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream);

@@ -23,7 +23,7 @@ SYMBOLS = [
     "pasn_packed_weights_bytes", "pasn_pack_weights", "pasn_head_forward", "pasn_occurrence_only",
     "pasn_push_record_bytes", "pasn_push_init", "pasn_push_decode", "pasn_push_reduce", "pasn_push_write_prototypes",
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
-    "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant",
+    "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant", "pasn_debug_fault", "pasn_debug_set_fault",
     "pasn_head_backward_workspace_bytes", "pasn_head_backward", "pasn_similarity_stats", "pasn_occurrence_lnorm",
 ]
 
@@ -109,6 +109,9 @@ def load() -> C.CDLL:
     lib.pasn_occurrence_lnorm.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]
     lib.pasn_debug_set_k1_variant.restype = C.c_int
     lib.pasn_debug_set_k1_variant.argtypes = [C.c_int]
+    lib.pasn_debug_fault.restype = C.c_int
+    lib.pasn_debug_set_fault.restype = C.c_int
+    lib.pasn_debug_set_fault.argtypes = [C.c_int]
     lib.pasn_debug_sm100_error.restype = C.c_int
     lib.pasn_debug_sm100_error.argtypes = [vp, C.POINTER(PasnDims), vp]
     if lib.pasn_abi_version() != 2:

@@ -36,6 +36,33 @@ static int resolve_family(const pasn_dims& d, int* err) {
   }
 }
 
+// ---- sticky fault word: pinned host memory mapped into the device address space -------------------
+static volatile int* g_fault_host = nullptr;
+static int* g_fault_dev = nullptr;
+namespace pasn {
+int* fault_word() {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    int* h = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      *h = 0;
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) { g_fault_host = h; g_fault_dev = reinterpret_cast<int*>(d); }
+    }
+    (void)cudaGetLastError();
+  }
+  return g_fault_dev;
+}
+}  // namespace pasn
+static inline bool faulted() { return g_fault_host != nullptr && *g_fault_host != 0; }
+extern "C" int pasn_debug_fault(void) { return g_fault_host ? *g_fault_host : 0; }
+extern "C" int pasn_debug_set_fault(int code) {
+  if (fault_word() == nullptr) return PASN_ERR_CUDA;
+  *g_fault_host = code;
+  return PASN_OK;
+}
+
 // ---- measurement hooks ------------------------------------------------------------------------
 static unsigned long long g_launches = 0;
 static int g_time_main = 0;
@@ -85,6 +112,7 @@ extern "C" int pasn_head_backward(const void* feat, const pasn_weights* w, const
                                   const float* grad_similarity, const float* grad_occurrence, const pasn_grads* grads,
                                   float* grad_feat, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dims_ok(dims) || !w || !grads) return PASN_ERR_INVALID;
+  if (faulted()) return PASN_ERR_FAULT;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
   const float* const* gp = reinterpret_cast<const float* const*>(grads);
@@ -112,6 +140,7 @@ extern "C" const char* pasn_strerror(int status) {
     case PASN_ERR_CUDA: return "CUDA runtime call or kernel launch failed";
     case PASN_ERR_UNSUPPORTED: return "requested kernel path is not available for these dims";
     case PASN_ERR_ALIGN: return "pointer alignment requirement violated";
+    case PASN_ERR_FAULT: return "an earlier kernel reported an internal pipeline fault (bounded wait expired); results are invalid";
     default: return "unknown pasn status";
   }
 }
@@ -157,6 +186,7 @@ extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const 
                                  float* distance, const pasn_push_args* push, void* workspace, size_t workspace_bytes,
                                  void* stream) {
   if (!dims_ok(dims) || !w || !logits || !similarity) return PASN_ERR_INVALID;
+  if (faulted()) return PASN_ERR_FAULT;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
   if (push && (!push->labels || !push->proto_class || !push->best_key)) return PASN_ERR_INVALID;   // best_vec is optional
@@ -181,6 +211,7 @@ extern "C" int pasn_head_forward(const void* feat, const pasn_weights* w, const 
 extern "C" int pasn_occurrence_only(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
                                     void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dims_ok(dims) || !w || !occurrence_map) return PASN_ERR_INVALID;
+  if (faulted()) return PASN_ERR_FAULT;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
   if (dims->path == PASN_PATH_TILED && !(tiled_supported(*dims) && packed)) return PASN_ERR_UNSUPPORTED;

@@ -112,6 +112,7 @@ void sm100_set_k1_variant(int variant);
 
 // ---- debug / measurement hooks (abi.cu) -----------------------------------------------------
 namespace pasn {
+int* fault_word();                                // device-visible alias of the host-mapped sticky fault word (or nullptr)
 void count_launch(int n = 1);                     // every kernel launch of the library is counted
 void main_kernel_begin(cudaStream_t st);          // bracket the dominant kernel with CUDA events when enabled
 void main_kernel_end(cudaStream_t st);

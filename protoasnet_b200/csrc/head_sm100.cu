@@ -57,6 +57,7 @@ struct K2Params {
   float* stash;   // push capture: [gridDim][P][256] fp32, FE row of this CTA's best clip per prototype (or null)
   int N, P, PP, K, cpt, ntiles;   // PP = padded P (row stride inside a tile), cpt = clips per tile = 128 / PP
   int* err;
+  int* fault;         // host-mapped sticky fault word (or null)
   long long* trace;   // optional: K2 stamps of CTA 0 at trace[768 ...] (see tools/trace_k2.py)
 };
 __device__ __forceinline__ long long gtimer_ns() {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   float* s_v = reinterpret_cast<float*>(smem + K2_SM_V);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Ctx ctx{p.err, abort_s};
+  Ctx ctx{p.err, abort_s, p.fault};
   if ((smem_u32(smem) & 1023u) != 0) {
     if (tid == 0) atomicCAS(p.err, 0, 901);
     return;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
           for (int c = tile * p.cpt; c < c1 && ok; ++c) {
             while (ld_acquire_gpu(p.ready + c) < K1_READY_TARGET) {
               __nanosleep(100);
-              if (*abort_s || clock64() - t0 > 8000000000ll) { *abort_s = 1; atomicCAS(p.err, 0, 612); ok = false; break; }
+              if (*abort_s || clock64() - t0 > 8000000000ll) { *abort_s = 1; atomicCAS(p.err, 0, 612); if (p.fault) *reinterpret_cast<volatile int*>(p.fault) = 612; ok = false; break; }
             }
           }
           if (!ok) break;
@@ -600,12 +601,13 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.clips_per_cta = ceil_div(L.Nv, num_sms);
   k1.cpt = TILE_M / k2_ppad(d);
   k1.err = err;
+  k1.fault = fault_word();
   k1.trace = g_trace;
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
   static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return e ? atoi(e) : 1; }();
   static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 1; }();
   k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
-  static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 1; }();
+  static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 0; }();
   k1.ready = ready;
   const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
@@ -643,6 +645,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k2.PP = k2_ppad(d);
   k2.ntiles = L.tiles2;
   k2.err = err;
+  k2.fault = k1.fault;
   k2.trace = g_trace;
   k2.a_kmajor = flush_kmajor; k2.l2_hints = l2_hints;
   k2.ready = k2_early ? ready : nullptr; k2.cpc = k1.clips_per_cta; k2.grid1 = grid1;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   const int ntok = ncl * S;
   const int ntiles = (ntok + TILE_M - 1) / TILE_M;
   const PackedLayout PL = packed_layout(p.C);
-  Ctx ctx{p.err, abort_s};
+  Ctx ctx{p.err, abort_s, p.fault};
   const bool two_phase = p.phases != 1;
 
   if ((smem_u32(smem) & 1023u) != 0) {  // swizzled layouts need the 1024-byte alignment we asked for

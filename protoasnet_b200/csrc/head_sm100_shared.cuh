@@ -48,6 +48,7 @@ struct K1Params {
   // SR the real voxel count per clip (= row pitch of the feature map and of the occurrence map).  G = 1: no split.
   int G, SR;
   int* err;
+  int* fault;                  // host-mapped sticky fault word (or null)
   long long* trace;            // optional [3][16][16] clock64 stamps of CTA 0 (MMA thread, epilogue warp 4)
   int phases;                  // two-phase kernel: 2 = G / A phases overlapped with the previous chain, 1 = serial order
   int dbg_skip;                // timing experiments only: bit0 = do not copy weight stages, bit1 = do not gather X,
@@ -62,17 +63,19 @@ struct K1Params {
 struct Ctx {
   int* err;
   volatile int* abort_s;
+  int* fault;   // host-mapped sticky fault word (may be null)
 };
 
 // bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug.  The spin is
 // out of line so that the fast path at every call site is a single try_wait.
-static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, int* err, volatile int* abort_s, int code) {
+static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, int* err, volatile int* abort_s, int* fault, int code) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*abort_s) return false;
     if (clock64() - t0 > 4000000000ll) {
       *abort_s = 1;
       atomicCAS(err, 0, code);
+      if (fault != nullptr) *reinterpret_cast<volatile int*>(fault) = code;
       return false;
     }
   }
@@ -80,7 +83,7 @@ static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, i
 }
 __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
   if (mbar_try_wait(bar, parity)) return true;
-  return bwait_slow(bar, parity, c.err, c.abort_s, code);
+  return bwait_slow(bar, parity, c.err, c.abort_s, c.fault, code);
 }
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {

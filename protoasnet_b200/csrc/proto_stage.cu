@@ -17,66 +17,62 @@ namespace pasn {
 constexpr int PS_THREADS = 256;
 constexpr int PS_WARPS = PS_THREADS / 32;
 
-// One block walks clips n = blockIdx.x, blockIdx.x + gridDim.x, ...; warp w handles prototypes w, w+8, ...
-// dynamic smem: float s_sim[P]; unsigned long long s_key[P] (push only)
-__global__ void __launch_bounds__(PS_THREADS) proto_stage_kernel(
-    const float* __restrict__ feats, const float* __restrict__ protos, const float* __restrict__ last_layer, int N,
-    int P, int D, int K, float* __restrict__ logits, float* __restrict__ sim, float* __restrict__ dist,
-    const int64_t* __restrict__ labels, const int32_t* __restrict__ proto_class, long long global_offset,
-    unsigned long long* __restrict__ best_key) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
-  float* s_sim = reinterpret_cast<float*>(smem_raw + (size_t)P * sizeof(unsigned long long));
+// One warp per (clip, prototype) row: cosine vs the prototype vector, (cos+1)/2, 1-s, push key.  Rows are spread over
+// the whole grid (N*P rows / 8 per block), so P = 40 and P = 4096 both fill the machine.
+__global__ void __launch_bounds__(PS_THREADS) proto_rows_kernel(
+    const float* __restrict__ feats, const float* __restrict__ protos, long long rows, int P, int D,
+    float* __restrict__ sim, float* __restrict__ dist, const int64_t* __restrict__ labels,
+    const int32_t* __restrict__ proto_class, long long global_offset, unsigned long long* __restrict__ best_key) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool do_push = best_key != nullptr;
-  if (do_push)
-    for (int p = threadIdx.x; p < P; p += PS_THREADS) s_key[p] = PASN_KEY_NONE;
-  __syncthreads();
-
-  for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    const long long label = do_push ? labels[n] : 0;
-    for (int p = warp; p < P; p += PS_WARPS) {
-      const float* f = feats + ((size_t)n * P + p) * D;
-      const float* v = protos + (size_t)p * D;
-      float ff = 0.f, vv = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        float a = f[d], b = v[d];
-        ff = fmaf(a, a, ff);
-        vv = fmaf(b, b, vv);
-      }
-      ff = warp_sum(ff);
-      vv = warp_sum(vv);
-      const float nf = fmaxf(sqrtf(ff), 1e-8f), nv = fmaxf(sqrtf(vv), 1e-8f);
-      float dot = 0.f;
-      for (int d = lane; d < D; d += 32) dot = fmaf(f[d] / nf, v[d] / nv, dot);
-      dot = warp_sum(dot);
-      if (lane == 0) {
-        const float s = (dot + 1.0f) / 2.0f;
-        const float dd = 1.0f - s;
-        s_sim[p] = s;
-        sim[(size_t)n * P + p] = s;
-        if (dist) dist[(size_t)n * P + p] = dd;
-        if (do_push) {
-          const int pc = proto_class[p];
-          if (pc < 0 || (long long)pc == label) {
-            unsigned long long key = pack_key(dd, (uint32_t)(global_offset + n));
-            if (key < s_key[p]) s_key[p] = key;  // prototype p is owned by exactly one warp of this block
-          }
+  for (long long r = (long long)blockIdx.x * PS_WARPS + warp; r < rows; r += (long long)gridDim.x * PS_WARPS) {
+    const long long n = r / P;
+    const int p = (int)(r - n * P);
+    const float* f = feats + (size_t)r * D;
+    const float* v = protos + (size_t)p * D;
+    float ff = 0.f, vv = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float a = f[d], b = v[d];
+      ff = fmaf(a, a, ff);
+      vv = fmaf(b, b, vv);
+    }
+    ff = warp_sum(ff);
+    vv = warp_sum(vv);
+    const float nf = fmaxf(sqrtf(ff), 1e-8f), nv = fmaxf(sqrtf(vv), 1e-8f);
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(f[d] / nf, v[d] / nv, dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      const float s = (dot + 1.0f) / 2.0f;
+      const float dd = 1.0f - s;
+      sim[r] = s;
+      if (dist) dist[r] = dd;
+      if (best_key != nullptr) {
+        const int pc = proto_class[p];
+        if (pc < 0 || (long long)pc == labels[n]) {
+          const unsigned long long key = pack_key(dd, (uint32_t)(global_offset + n));
+          // plain read as a filter (the value only ever decreases), atomic only for candidates
+          if ((long long)(key ^ PASN_KEY_SIGN) < *reinterpret_cast<volatile long long*>(best_key + p))
+            key_atomic_min_global(&best_key[p], key);
         }
       }
     }
-    __syncthreads();
+  }
+}
+
+// logits[n,k] = sum_p sim[n,p] * last_layer[k,p]: one block per clip, one warp per class
+__global__ void __launch_bounds__(PS_THREADS) proto_logits_kernel(const float* __restrict__ sim,
+                                                                  const float* __restrict__ last_layer, int N, int P, int K,
+                                                                  float* __restrict__ logits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const float* s = sim + (size_t)n * P;
     for (int k = warp; k < K; k += PS_WARPS) {
       float acc = 0.f;
-      for (int p = lane; p < P; p += 32) acc = fmaf(s_sim[p], last_layer[(size_t)k * P + p], acc);
+      for (int p = lane; p < P; p += 32) acc = fmaf(s[p], last_layer[(size_t)k * P + p], acc);
       acc = warp_sum(acc);
       if (lane == 0) logits[(size_t)n * K + k] = acc;
     }
-    __syncthreads();
   }
-  if (do_push)
-    for (int p = threadIdx.x; p < P; p += PS_THREADS)
-      if (s_key[p] != PASN_KEY_NONE) key_atomic_min_global(&best_key[p], s_key[p]);
 }
 
 // best_vec[p,:] = feats[n*,p,:] where n* = clip of this call that holds best_key[p] (keys carry the global clip index);
@@ -95,16 +91,15 @@ __global__ void push_capture_dense_kernel(const unsigned long long* __restrict__
 int launch_proto_stage(const float* feats, const float* protos, const float* last_layer, int N, int P, int D, int K,
                        float* logits, float* sim, float* dist, const pasn_push_args* push, cudaStream_t st) {
   if (N <= 0) return PASN_OK;
-  size_t smem = (size_t)P * (sizeof(unsigned long long) + sizeof(float));
-  if (smem > 200 * 1024) return PASN_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
-    if (cudaFuncSetAttribute(proto_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return PASN_ERR_CUDA;
-  int grid = N < 148 * 8 ? N : 148 * 8;
-  proto_stage_kernel<<<grid, PS_THREADS, smem, st>>>(
-      feats, protos, last_layer, N, P, D, K, logits, sim, dist, push ? push->labels : nullptr,
-      push ? push->proto_class : nullptr, push ? (long long)push->global_offset : 0,
-      push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr);
+  const long long rows = (long long)N * P;
+  long long blocks = (rows + PS_WARPS - 1) / PS_WARPS;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  proto_rows_kernel<<<(unsigned)blocks, PS_THREADS, 0, st>>>(
+      feats, protos, rows, P, D, sim, dist, push ? push->labels : nullptr, push ? push->proto_class : nullptr,
+      push ? (long long)push->global_offset : 0, push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  proto_logits_kernel<<<N < 148 * 8 ? N : 148 * 8, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
   PASN_LAUNCH_CHECK();
   count_launch();
   if (push && push->best_vec) {   // winner capture in the same pass (push_abs_revision.py:299-302)

@@ -65,7 +65,7 @@ static __device__ __noinline__ bool wait_slow(uint64_t* bar, uint32_t parity, in
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
-      atomicCAS(err, 0, code);
+      *reinterpret_cast<volatile int*>(err) = code;
       return false;
     }
   }
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   const Gemm& g = kp.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((smem_u32(smem) & 1023u) != 0) {
-    if (tid == 0) atomicCAS(kp.err, 0, 700);
+    if (tid == 0) *reinterpret_cast<volatile int*>(kp.err) = 700;
     return;
   }
   if (tid == 0) {
@@ -380,18 +380,17 @@ bool lo_planes_f16() {
 int launch(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;
   if (g.npass < 1 || g.npass > 4 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
-  static int* d_err = nullptr;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return PASN_ERR_CUDA;
-    if (cudaMalloc(&d_err, 256) != cudaSuccess) return PASN_ERR_CUDA;   // one-time, 256-byte fault word (never freed)
-    if (cudaMemset(d_err, 0, 256) != cudaSuccess) return PASN_ERR_CUDA;
     attr_done = true;
   }
+  int* fault = fault_word();   // bounded waits report into the host-mapped sticky fault word
+  if (fault == nullptr) return PASN_ERR_CUDA;
   KParams kp;
   kp.g = g;
-  kp.err = d_err;
+  kp.err = fault;
   kp.tiles_m = ceil_div(g.M, BM);
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);

@@ -415,3 +415,25 @@ def test_small_batch_voxel_group_split_matches_unsplit():
         assert torch.equal(small["occurrence_map"], big["occurrence_map"][:n])      # per-voxel results do not depend on the split
         assert_close(small["similarity"], big["similarity"][:n].cpu().numpy(), 1e-4, f"split vs unsplit n={n}")
         assert_close(small["features_extracted"], big["features_extracted"][:n].cpu().numpy(), 1e-4, f"features n={n}")
+
+
+def test_sticky_fault_word_is_surfaced_without_debug_sync():
+    """A kernel that gives up on a bounded wait writes a code into the host-mapped fault word; every later compute call
+    must then fail loudly (PASN_ERR_FAULT) instead of returning garbage with status 0 -- no PASN_DEBUG_SYNC needed."""
+    dims = synth.CONFIGS["tiny_video"]
+    m = build_model(dims, synth.make_head_params(dims, seed=1))
+    x = torch.zeros((2, dims.C) + dims.spatial, device="cuda")
+    lib = _lib.load()
+    with torch.no_grad():
+        m(x)
+    assert lib.pasn_debug_fault() == 0
+    try:
+        assert lib.pasn_debug_set_fault(612) == 0
+        with torch.no_grad(), pytest.raises(_lib.PasnError, match="fault"):
+            m(x)
+        with torch.no_grad(), pytest.raises(_lib.PasnError, match="fault"):
+            m.compute_occurence_map(x)
+    finally:
+        lib.pasn_debug_set_fault(0)
+    with torch.no_grad():
+        m(x)
