@@ -11,9 +11,6 @@
 //
 // Every mbarrier wait is bounded: a protocol fault becomes an error code in *err, not a hung GPU.
 #include <cuda.h>
-#include <cuda_fp16.h>
-
-#include <cstdlib>
 
 #include "sm100_prims.cuh"
 #include "tc_gemm.cuh"
@@ -76,6 +73,7 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, 
   return wait_slow(bar, parity, err, code);
 }
 
+__device__ __forceinline__ float tv(const Output& o, float v) { return o.absval ? fabsf(v) : v; }
 __device__ __forceinline__ float act_apply(float v, int act) {
   return act == ACT_RELU ? fmaxf(v, 0.f) : (act == ACT_ABS ? fabsf(v) : v);
 }
@@ -118,18 +116,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
         const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
         const int m0 = (r / kp.tiles_n) * BM, n0 = (r % kp.tiles_n) * bn;
+        const bool split_k = g.k_rows_per_batch > 0;
+        const int krow0 = split_k ? b * g.k_rows_per_batch : 0;
         for (int pass = 0; pass < g.npass && ok; ++pass) {
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_EMPTY + s], ph ^ 1, kp.err, 701))) break;
             const uint32_t dst = sbase + s * STAGE_BYTES;
             mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
-            tma_load_3d(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
+            const int krow = krow0 + kb * BK;   // K coordinate of MN-major operands (rows)
+            if (!g.a_mn_major) {
+              tma_load_3d(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
+            } else {
+              for (int j = 0; j < 2; ++j)
+                tma_load_3d(dst + j * 8192, &kp.tmA, g.a_off[pass] + m0 + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
+                            &bars[B_FULL + s]);
+            }
             if (!g.b_mn_major) {
               tma_load_3d(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
             } else {
               for (int j = 0; j < bn / 64; ++j)
-                tma_load_3d(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, kb * BK, g.b_batched ? b : 0,
-                            &bars[B_FULL + s]);
+                tma_load_3d(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
+                            (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s]);
             }
             s = s + 1 == STAGES ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
@@ -140,9 +147,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      uint32_t idesc[4];
-      for (int q = 0; q < 4; ++q)
-        idesc[q] = make_idesc_16(BM, (uint32_t)bn, g.a_f16[q] ? 0u : 1u, g.b_f16[q] ? 0u : 1u, 0, g.b_mn_major ? 1u : 0u);
+      const uint32_t id = make_idesc_16(BM, (uint32_t)bn, 1u, 1u, g.a_mn_major ? 1u : 0u, g.b_mn_major ? 1u : 0u);
+      const uint32_t a_lbo = g.a_mn_major ? 8192u : 16u, a_kstep = g.a_mn_major ? 128u : 2u;
       constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
       const uint32_t b_lbo = g.b_mn_major ? 8192u : 16u, b_kstep = g.b_mn_major ? 128u : 2u;
       const uint32_t bar0 = smem_u32(bars);
@@ -155,14 +161,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         tc_fence_after();
         const uint32_t d = tbase + 256u * buf;
         for (int pass = 0; pass < g.npass && ok; ++pass) {
-          const uint32_t id = idesc[pass];
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
             tc_fence_after();
             const uint32_t sa = sbase + s * STAGE_BYTES;
-            const uint32_t alo = desc_lo(sa, 16), blo = desc_lo(sa + A_BYTES, b_lbo);
+            const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + A_BYTES, b_lbo);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * 2, HI, blo + k4 * b_kstep, HI, id, (pass | kb | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, id, (pass | kb | k4) ? 1u : 0u);
             mma_commit_a(bar0 + 8u * (B_EMPTY + s));
             s = s + 1 == STAGES ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
@@ -197,8 +202,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[32 * bx + 4 * c]), "f"(v[32 * bx + 4 * c + 1]),
-                         "f"(v[32 * bx + 4 * c + 2]), "f"(v[32 * bx + 4 * c + 3])
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(tv(o, v[32 * bx + 4 * c])),
+                         "f"(tv(o, v[32 * bx + 4 * c + 1])), "f"(tv(o, v[32 * bx + 4 * c + 2])), "f"(tv(o, v[32 * bx + 4 * c + 3]))
                          : "memory");
           }
         } else {
@@ -207,13 +212,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
-              if (o.mode == OUT_BF16_HILO && bx == 1) {
-                const float l0 = a0 - round_bf16(a0), l1 = a1 - round_bf16(a1);
-                pk[j] = g.lo_f16 ? pack_f16x2(l0, l1) : pack_bf16x2(l0, l1);
-              } else {
-                pk[j] = pack_bf16x2(a0, a1);
-              }
+              const float a0 = tv(o, v[8 * c + 2 * j]), a1 = tv(o, v[8 * c + 2 * j + 1]);
+              pk[j] = (o.mode == OUT_BF16_HILO && bx == 1) ? pack_bf16x2(a0 - round_bf16(a0), a1 - round_bf16(a1)) : pack_bf16x2(a0, a1);
             }
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -238,17 +238,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       for (int j = 0; j < 64; ++j) {
         const int col = col0 + j;
         if (col >= ncols) continue;
+        const float x = tv(o, v[j]);
         if (o.mode == OUT_F32) {
-          reinterpret_cast<float*>(o.ptr)[base + col] = v[j];
+          reinterpret_cast<float*>(o.ptr)[base + col] = x;
         } else {
           __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
-          const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+          const __nv_bfloat16 hi = __float2bfloat16_rn(x);
           p16[base + col] = hi;
-          if (o.mode == OUT_BF16_HILO) {
-            const float l = v[j] - __bfloat162float(hi);
-            if (g.lo_f16) reinterpret_cast<__half*>(o.ptr)[base + o.lo_off + col] = __float2half_rn(l);
-            else p16[base + o.lo_off + col] = __float2bfloat16_rn(l);
-          }
+          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
         }
       }
     };
@@ -307,6 +304,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           v[4 * j4 + 1] = act_apply(fmaf(rowterm, cc.y, v[4 * j4 + 1] + bb.y), g.act);
           v[4 * j4 + 2] = act_apply(fmaf(rowterm, cc.z, v[4 * j4 + 2] + bb.z), g.act);
           v[4 * j4 + 3] = act_apply(fmaf(rowterm, cc.w, v[4 * j4 + 3] + bb.w), g.act);
+        }
+        if (g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr) {
+          // element-wise epilogue inputs (backward: + upstream gradient, * sign of the |.| argument, ReLU mask)
+          if (row_ok) {
+            const float* ad = g.addin.ptr ? reinterpret_cast<const float*>(g.addin.ptr) + (long long)b * g.addin.bs + (long long)row * g.addin.ld : nullptr;
+            const __nv_bfloat16* sg = g.signin.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.signin.ptr) + (long long)b * g.signin.bs + (long long)row * g.signin.ld : nullptr;
+            const __nv_bfloat16* mk = g.mask.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.mask.ptr) + (long long)b * g.mask.bs + (long long)row * g.mask.ld : nullptr;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const int col = col0 + j;
+              if (col < g.N) {
+                if (ad) v[j] += __ldg(ad + col);
+                if (sg) { const float x = __bfloat162float(sg[col]); v[j] = x > 0.f ? v[j] : (x < 0.f ? -v[j] : 0.f); }
+                if (mk) v[j] = __bfloat162float(mk[col]) > 0.f ? v[j] : 0.f;
+              }
+            }
+          }
         }
         if (g.psum != nullptr) {
           const bool rounded = g.psum_rounded != 0;
@@ -372,10 +386,7 @@ bool out_aligned(const Output& o) {
 }  // namespace
 
 bool available() { return encode_fn() != nullptr; }
-bool lo_planes_f16() {
-  static const bool v = [] { const char* e = getenv("PASN_TILED_LO"); return !(e && e[0] == 'b'); }();
-  return v;
-}
+
 
 int launch(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;
@@ -394,16 +405,25 @@ int launch(const Gemm& g, cudaStream_t st) {
   kp.tiles_m = ceil_div(g.M, BM);
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);
-  if (!make_map(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, (unsigned long long)g.ka, (unsigned long long)g.M,
-                g.a_batched ? g.batch : 1, (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, BK, BM))
-    return PASN_ERR_ALIGN;
+  const bool split_k = g.k_rows_per_batch > 0;
+  if (split_k && !(g.a_mn_major && g.b_mn_major)) return PASN_ERR_INVALID;
+  if (!g.a_mn_major) {
+    if (!make_map(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, (unsigned long long)g.ka, (unsigned long long)g.M,
+                  g.a_batched ? g.batch : 1, (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, BK, BM))
+      return PASN_ERR_ALIGN;
+  } else {   // [batch][K rows][ka columns], m contiguous: boxes of 64 m x 64 k
+    if (!make_map(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, (unsigned long long)g.ka,
+                  (unsigned long long)(g.a_rows ? g.a_rows : g.K), (g.a_batched && !split_k) ? g.batch : 1,
+                  (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, 64, BK))
+      return PASN_ERR_ALIGN;
+  }
   if (!g.b_mn_major) {
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
                   (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)g.bn))
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
-                  (unsigned long long)(g.b_rows ? g.b_rows : g.K), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.K), (g.b_batched && !split_k) ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
       return PASN_ERR_ALIGN;
   }
   for (int mi = 0; mi < 2; ++mi) {

@@ -12,8 +12,6 @@
 //   FE = pooled W2^T + (sum_s O[p,s]) b2     W2 applied after pooling (exact in real arithmetic)
 //   cosine / (.+1)/2 / logits / 1-s / push keys: proto_stage.cu (fp32)
 // Hidden activations are bf16 in HBM between the GEMMs (hi|lo planes in fp32 mode).
-#include <cuda_fp16.h>
-
 #include "tc_gemm.cuh"
 
 namespace pasn {
@@ -78,19 +76,15 @@ PackLayout pack_layout(const pasn_dims& d) {
   return L;
 }
 
-// fp32 [rows][cols] -> 16-bit planes [rows][ex*cols]: plane 0 = bf16(w), plane 1 = fp16(w - plane 0)
-__device__ __forceinline__ void store_lo(__nv_bfloat16* p, float l, int f16) {
-  if (f16) *reinterpret_cast<__half*>(p) = __float2half_rn(l);
-  else *p = __float2bfloat16_rn(l);
-}
-__global__ void pack_planes_kernel(const float* __restrict__ w, int rows, int cols, int ex, int f16, __nv_bfloat16* __restrict__ out) {
+// fp32 [rows][cols] -> bf16 planes [rows][ex*cols]: plane 0 = bf16(w), plane 1 = bf16(w - plane 0)
+__global__ void pack_planes_kernel(const float* __restrict__ w, int rows, int cols, int ex, __nv_bfloat16* __restrict__ out) {
   const long long n = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
     const float v = w[i];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     out[(size_t)r * ex * cols + c] = hi;
-    if (ex == 2) store_lo(out + (size_t)r * ex * cols + cols + c, v - __bfloat162float(hi), f16);
+    if (ex == 2) *(out + (size_t)r * ex * cols + cols + c) = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 __global__ void pack_bias_kernel(const float* __restrict__ b, int n, int round, float* __restrict__ out) {
@@ -101,7 +95,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int n, int round, 
 // feature map -> token-major bf16 planes XT[(n*S + s)][ex*C]
 //   NCS ([n][C][S]): 32x32 tile transpose through shared memory;  NSC fp32 ([n][S][C]): plane split only
 template <typename T>
-__global__ void to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int ex, int f16, __nv_bfloat16* __restrict__ out) {
+__global__ void to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int ex, __nv_bfloat16* __restrict__ out) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
   const T* xn = x + (size_t)n * C * S;
@@ -117,11 +111,11 @@ __global__ void to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int 
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       __nv_bfloat16* row = out + ((size_t)n * S + s) * ex * C;
       row[c] = hi;
-      if (ex == 2) store_lo(row + C + c, v - __bfloat162float(hi), f16);
+      if (ex == 2) *(row + C + c) = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
   }
 }
-__global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long rows, int C, int f16, __nv_bfloat16* __restrict__ out) {
+__global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long rows, int C, __nv_bfloat16* __restrict__ out) {
   const long long n = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
@@ -129,20 +123,18 @@ __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long 
     const float v = x[i];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     out[r * 2 * C + c] = hi;
-    store_lo(out + r * 2 * C + C + c, v - __bfloat162float(hi), f16);
+    *(out + r * 2 * C + C + c) = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
-// passes of a product of two operands that each come as planes (hi bf16 at column 0, lo fp16 at column *_lo)
+// passes of a product of two operands that each come as planes (hi at column 0, lo at column *_lo)
 void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo) {
-  for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = g.a_f16[q] = g.b_f16[q] = 0;
-  g.lo_f16 = tcg::lo_planes_f16() ? 1 : 0;
+  for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = 0;
   if (ex == 1) { g.npass = 1; return; }
-  const int f = tcg::lo_planes_f16() ? 1 : 0;
   g.npass = 4;                                   // hi*hi, hi*lo, lo*hi, lo*lo
-  g.b_off[1] = b_lo; g.b_f16[1] = f;
-  g.a_off[2] = a_lo; g.a_f16[2] = f;
-  g.a_off[3] = a_lo; g.a_f16[3] = f; g.b_off[3] = b_lo; g.b_f16[3] = f;
+  g.b_off[1] = b_lo;
+  g.a_off[2] = a_lo;
+  g.a_off[3] = a_lo; g.b_off[3] = b_lo;
 }
 
 }  // namespace
@@ -161,7 +153,7 @@ int tiled_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, 
   const int ex = d.dtype == PASN_F32 ? 2 : 1, D2 = d.D / 2;
   char* pk = reinterpret_cast<char*>(packed);
   auto planes = [&](const float* src, int rows, int cols, size_t off) {
-    pack_planes_kernel<<<148 * 2, 256, 0, st>>>(src, rows, cols, ex, tcg::lo_planes_f16() ? 1 : 0, reinterpret_cast<__nv_bfloat16*>(pk + off));
+    pack_planes_kernel<<<148 * 2, 256, 0, st>>>(src, rows, cols, ex, reinterpret_cast<__nv_bfloat16*>(pk + off));
     count_launch();
   };
   planes(w.addon_w1, d.D, d.C, L.off_w13);
@@ -201,13 +193,12 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     if (((uintptr_t)xt & 15) != 0) return PASN_ERR_ALIGN;
   } else {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ws + p.off_xt);
-    const int f16 = tcg::lo_planes_f16() ? 1 : 0;
     if (d.layout == PASN_LAYOUT_NSC) {
-      to_tokens_nsc_f32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, C, f16, dst);
+      to_tokens_nsc_f32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, C, dst);
     } else {
       dim3 grid(ceil_div(S, 32), ceil_div(C, 32), nb), block(32, 8);
-      if (ex == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, f16, dst);
-      else to_tokens_ncs_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, f16, dst);
+      if (ex == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, dst);
+      else to_tokens_ncs_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, dst);
     }
     PASN_LAUNCH_CHECK();
     count_launch();
@@ -304,7 +295,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.B = W2; g.ldb = (long long)ex * D; g.b_batched = 0; g.kb = ex * D;
     g.M = nb * P; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
     set_passes(g, ex, D, D);
-    if (ex == 1) { g.npass = 2; g.a_off[1] = D; g.a_f16[1] = g.lo_f16; }   // pooled = hi + lo planes, W2 bf16
+    if (ex == 1) { g.npass = 2; g.a_off[1] = D; }   // pooled = hi + lo planes, W2 bf16
     g.rowparts = PSUM; g.nparts = 2 * p.tiles_n_c; g.colvec = b2;
     g.act = tcg::ACT_NONE;
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};

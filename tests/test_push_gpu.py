@@ -9,7 +9,7 @@ import torch
 from oracle import push_oracle as po
 from protoasnet_b200 import push as pushmod
 from protoasnet_b200 import synth
-from tests.util import BF16_RTOL, FP32_RTOL, assert_close, build_model, load_golden
+from tests.util import BF16_RTOL, FP32_RTOL, FP32_TC_FEAT_ATOL, assert_close, build_model, feat_atol, load_golden
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -45,13 +45,14 @@ def test_push_prototypes_matches_reference_golden(path, tmp_path):
     res = pushmod.push_prototypes(loader, m, class_specific=True, abstain_class=r["abstain_class"],
                                   root_dir_for_saving_prototypes=str(tmp_path), epoch_number="t", log=lambda *a: None)
     assert np.array_equal(res["index"].cpu().numpy(), z["winner_index"])           # bit-exact indices
-    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors")
+    fa = feat_atol(m, torch.from_numpy(x[:1]).cuda())
+    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors", atol_frac=fa)
     assert_close(1 - res["distance"].double(), z["winner_similarity"], FP32_RTOL, "winner similarity")
     import pickle
     info = pickle.load(open(os.path.join(str(tmp_path), "epoch-t", "prototypes_info.pickle"), "rb"))
     assert np.array_equal(info["prototypes_gts"], z["winner_gts"])
     assert_close(info["prototypes_preds"], z["winner_logits"], FP32_RTOL, "winner logits")
-    assert_close(info["prototypes_occurrence_maps"], z["winner_occurrence_maps"], FP32_RTOL, "winner occ maps")
+    assert_close(info["prototypes_occurrence_maps"], z["winner_occurrence_maps"], FP32_RTOL, "winner occ maps", atol_frac=fa)
     assert [str(s) for s in info["prototypes_filenames"]] == [f"clip_{i}" for i in z["winner_index"]]
 
 
@@ -66,7 +67,7 @@ def test_push_resident_matches_golden_and_no_replace(path, chunk):
     assert np.array_equal(res["index"].cpu().numpy(), z["winner_index"])
     assert torch.equal(m.prototype_vectors.data, before)                           # replace_prototypes=False
     pushmod.push_resident(m, xg, yg, chunk=chunk, abstain_class=r["abstain_class"], replace_prototypes=True)
-    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors")
+    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors", atol_frac=feat_atol(m, xg))
 
 
 def test_push_bf16_features_match_oracle_indices():
@@ -231,7 +232,8 @@ def test_agent_push_wrapper_matches_reference_golden(tmp_path):
     info = pickle.load(open(os.path.join(d, "prototypes_info.pickle"), "rb"))
     assert np.array_equal(info["prototypes_gts"], z["winner_gts"])
     pushmod.agent_push(_Agent())                                                    # default: prototypes replaced
-    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors")
+    assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], FP32_RTOL, "prototype_vectors",
+                 atol_frac=feat_atol(m, torch.from_numpy(x[:1]).cuda()))
 
 
 class _RandomWindowSet(torch.utils.data.Dataset):

@@ -9,6 +9,22 @@ from protoasnet_b200 import synth
 
 FP32_RTOL = 1e-5   # north_star: logits and similarities within 1e-5 relative in fp32
 BF16_RTOL = 1e-3   # ... and 1e-3 relative in bf16
+# fp32 feature maps on the tensor cores (tiled path: bf16 hi/lo split, 16 significant bits per operand, fp32 accumulation):
+# logits / similarities / distances keep north_star's 1e-5; the big intermediate tensors that are also outputs
+# (features_extracted, occurrence_map, pushed prototype_vectors) are judged against their scale at this fraction.
+# kernel_path = PASN_PATH_GENERIC (CUDA-core FFMA) is the path that meets 1e-6 of scale on those as well.
+FP32_TC_FEAT_ATOL = 3e-5
+
+
+def feat_atol(model, x):
+    """atol_frac for features_extracted / occurrence_map of ``model`` fed ``x``: None (default, rtol/10) unless an fp32 input
+    is served by a tensor-core path."""
+    import ctypes as C
+    from protoasnet_b200 import _lib
+    if x.dtype != torch.float32:
+        return None
+    dims = model._rt.make_dims(x, model.kernel_path)[0]
+    return FP32_TC_FEAT_ATOL if _lib.load().pasn_tcgen05_supported(C.byref(dims)) else None
 
 
 def build_model(dims: synth.HeadDims, sd_np, device="cuda", path=None):
