@@ -10,6 +10,9 @@
 //   O  = |W5 G2|            per clip, written straight in the [N,P,S] layout of occurrence_map   (occurrence_module[4], abs)
 //   pooled[p,:] = sum_s O[p,s] H1[:,s]     per clip, K = S; H1 (token-major) is the MN-major B operand
 //   FE = pooled W2^T + (sum_s O[p,s]) b2     W2 applied after pooling (exact in real arithmetic)
+//   ... when that is the cheaper order (P rows per clip, times the hi/lo passes of the pooled vectors, against S voxels);
+//   otherwise (image head: S = 49, config 5: P = 4096 > S) the reference's order is kept:
+//   F = W2 H1 + b2 over all tokens, FE[p,:] = sum_s O[p,s] F[:,s] straight out of the pooling GEMM in fp32.
 //   cosine / (.+1)/2 / logits / 1-s / push keys: proto_stage.cu (fp32)
 // Hidden activations are bf16 in HBM between the GEMMs (hi|lo planes in fp32 mode).
 #include "tc_gemm.cuh"
@@ -22,9 +25,10 @@ struct Plan {
   int ex;        // bf16 planes per activation / weight: 1 (bf16 mode), 2 (fp32 mode: hi | lo)
   int C, D, D2, P, K, S, Sp;   // Sp: column pitch of one plane of the pooling A operand (occurrence values)
   bool occ_direct;             // bf16 mode and 16-byte aligned rows: the pooling reads the occurrence_map buffer itself
+  bool w2_first;               // F = W2 H1 + b2 before the pooling (cheaper when S is small against P)
   int bn_c, tiles_n_c;         // tile width / count along S of the O GEMM (psum parts = 2 * tiles_n_c)
   int nb;                      // clips per chunk
-  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_fe, total;
+  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, total;
 };
 
 inline int pick_bn(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
@@ -34,12 +38,16 @@ Plan make_plan(const pasn_dims& d) {
   p.ex = d.dtype == PASN_F32 ? 2 : 1;
   p.C = d.C; p.D = d.D; p.D2 = d.D / 2; p.P = d.P; p.K = d.K; p.S = d.S;
   p.occ_direct = p.ex == 1 && (d.S * 2) % 16 == 0;
+  // MACs of the W2 stage per clip: S*D*D*passes before the pooling, P*D*D*passes after it (bf16 mode: the pooled vectors
+  // go in as hi + lo planes, two passes; fp32 mode: three passes either way)
+  p.w2_first = p.ex == 1 ? (d.S < 2 * d.P) : (d.S < d.P);
   p.Sp = p.ex == 2 ? (d.S + 63) / 64 * 64 : (d.S + 7) / 8 * 8;
   p.bn_c = pick_bn(p.ex == 2 ? p.Sp : d.S);
   p.tiles_n_c = ceil_div(p.ex == 2 ? p.Sp : d.S, p.bn_c);
   const size_t S = d.S, ex = p.ex;
   const size_t per_clip = S * ex * d.C * 2 + S * ex * 2 * d.D * 2 + S * ex * p.D2 * 2 + (size_t)d.P * ex * p.Sp * 2 +
-                          (size_t)d.P * 2 * p.tiles_n_c * 4 + (size_t)d.P * 2 * d.D * 2 + (size_t)d.P * d.D * 4 + 2048;
+                          (size_t)d.P * 2 * p.tiles_n_c * 4 + (size_t)d.P * 2 * d.D * 2 + S * ex * d.D * 2 +
+                          (size_t)d.P * d.D * 4 + 2048;
   long long nb = (long long)(((size_t)2 << 30) / per_clip);
   if (nb < 1) nb = 1;
   if (nb > d.N) nb = d.N > 0 ? d.N : 1;
@@ -51,7 +59,8 @@ Plan make_plan(const pasn_dims& d) {
   p.off_g2 = take((size_t)p.nb * S * ex * p.D2 * 2);
   p.off_occ = take((size_t)p.nb * d.P * ex * p.Sp * 2);
   p.off_psum = take((size_t)p.nb * d.P * 2 * p.tiles_n_c * 4);
-  p.off_pool = take((size_t)p.nb * d.P * 2 * d.D * 2);
+  p.off_pool = take(p.w2_first ? 0 : (size_t)p.nb * d.P * 2 * d.D * 2);
+  p.off_f = take(p.w2_first ? (size_t)p.nb * S * ex * d.D * 2 : 0);
   p.off_fe = take((size_t)p.nb * d.P * d.D * 4);
   p.total = o + 256;
   return p;
@@ -131,10 +140,11 @@ __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long 
 void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo) {
   for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = 0;
   if (ex == 1) { g.npass = 1; return; }
-  g.npass = 4;                                   // hi*hi, hi*lo, lo*hi, lo*lo
+  // hi*hi, hi*lo, lo*hi.  The lo*lo term is below the representation error of the split itself (each operand keeps 16
+  // significant bits: |x - xh - xl| <= 2^-17 |x|, and |xl wl| <= 2^-18 |x w|), so it is not computed.
+  g.npass = 3;
   g.b_off[1] = b_lo;
   g.a_off[2] = a_lo;
-  g.a_off[3] = a_lo; g.b_off[3] = b_lo;
 }
 
 }  // namespace
@@ -270,11 +280,37 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     } else if (!occ_only) {
       pool_a = reinterpret_cast<const __nv_bfloat16*>(occ_user); pool_lda = S;
     }
-    g.psum = occ_only ? nullptr : PSUM;
+    g.psum = (occ_only || p.w2_first) ? nullptr : PSUM;
     g.psum_rounded = ex == 1;
     if ((rc = tcg::launch(g, st))) return rc;
   }
   if (occ_only) return PASN_OK;
+  if (p.w2_first) {
+    // ---- (D') F = H1 W2^T + b2 over all tokens, then FE[n] = O[n] F[n] (K = S) straight into fp32
+    __nv_bfloat16* F = reinterpret_cast<__nv_bfloat16*>(ws + p.off_f);
+    {
+      tcg::Gemm g{};
+      g.A = Y; g.lda = (long long)ex * 2 * D; g.a_batched = 0; g.ka = ex * 2 * D;
+      g.B = W2; g.ldb = (long long)ex * D; g.b_batched = 0; g.kb = ex * D;
+      g.M = (int)T; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
+      set_passes(g, ex, 2 * D, D);
+      g.bias = b2; g.act = tcg::ACT_NONE;
+      g.out[0] = {F, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_BF16_HILO, (long long)ex * D, 0, D};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {
+      tcg::Gemm g{};
+      g.A = pool_a; g.lda = pool_lda; g.a_bs = (long long)P * pool_lda; g.a_batched = 1;
+      g.ka = ex == 2 ? 2 * p.Sp : S;
+      g.B = F; g.ldb = (long long)ex * D; g.b_bs = (long long)S * ex * D; g.b_batched = 1; g.kb = ex * D;
+      g.b_mn_major = 1; g.b_rows = S;
+      g.M = P; g.N = D; g.K = ex == 2 ? p.Sp : S; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
+      set_passes(g, ex, p.Sp, D);
+      g.act = tcg::ACT_NONE;
+      g.out[0] = {FE, tcg::OUT_F32, (long long)D, (long long)P * D, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+  } else {
   // ---- (D) pooled[n] = O[n] H1[n]   (K = S; H1 token-major = MN-major B operand) -> bf16 hi | lo planes
   {
     tcg::Gemm g{};
@@ -300,6 +336,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.act = tcg::ACT_NONE;
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};
     if ((rc = tcg::launch(g, st))) return rc;
+  }
   }
   // ---- cosine / similarity / logits / distance / push keys (+ winner capture)
   pasn_push_args pa;
