@@ -143,9 +143,9 @@ int pasn_head_forward(const void* feat, const pasn_weights* w, const void* packe
                       void* stream);
 
 /* Replaces Video_XProtoNet.compute_occurence_map minus the backbone (src/models/Video_XProtoNet.py:100-109; called once
- * more per training step by TransformLoss, src/loss/loss.py:302).  Runs the occurrence branch alone: on the tiled
- * tensor-core path when dims.path = PASN_PATH_TILED (`packed` = pasn_pack_weights with the same dims), on the generic
- * CUDA-core path otherwise (`packed` ignored). */
+ * more per training step by TransformLoss, src/loss/loss.py:302).  Served by the same kernel family as pasn_head_forward
+ * for these dims (`packed`, `workspace` as there): the fused token kernel alone (it writes the map on its way), the
+ * occurrence branch of the tiled GEMM chain, or the generic CUDA-core path (`packed` NULL or dims.path GENERIC). */
 int pasn_occurrence_only(const void* feat, const pasn_weights* w, const void* packed, const pasn_dims* dims,
                          void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -219,6 +219,11 @@ int pasn_debug_set_trace(void* device_buffer);
  * 1 = serial (default), 2 = two-phase (layer-1 phases overlapped with the previous tile's chain);
  * anything else = back to the default / PASN_K1_PHASES */
 int pasn_debug_set_k1_variant(int variant);
+/* Test hook for the building block of the tiled tensor-core path: one launch of the library's internal tcgen05 GEMM.
+ * `desc_host` points at a pasn::tcg::Gemm (protoasnet_b200/csrc/tc_gemm.cuh; tests/test_tc_gemm_gpu.py mirrors it field
+ * by field), `desc_bytes` must equal pasn_debug_tc_gemm_desc_bytes(). */
+size_t pasn_debug_tc_gemm_desc_bytes(void);
+int pasn_debug_tc_gemm(const void* desc_host, size_t desc_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 // extern "C" entry points of libpasn_b200.so (declared in include/pasn.h) and path dispatch.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 using namespace pasn;
 
@@ -130,6 +131,15 @@ extern "C" int pasn_debug_sm100_error(const void* workspace, const pasn_dims* di
 extern "C" int pasn_debug_set_trace(void* device_buffer) { sm100_set_trace(device_buffer); return PASN_OK; }
 extern "C" int pasn_debug_set_k1_variant(int variant) { sm100_set_k1_variant(variant); return PASN_OK; }
 
+// test hook: one launch of the internal tiled tcgen05 GEMM (descriptor = pasn::tcg::Gemm, see csrc/tc_gemm.cuh)
+extern "C" size_t pasn_debug_tc_gemm_desc_bytes(void) { return sizeof(tcg::Gemm); }
+extern "C" int pasn_debug_tc_gemm(const void* desc_host, size_t desc_bytes, void* stream) {
+  if (!desc_host || desc_bytes != sizeof(tcg::Gemm)) return PASN_ERR_INVALID;
+  if (faulted()) return PASN_ERR_FAULT;
+  if (!tcg::available()) return PASN_ERR_UNSUPPORTED;
+  return tcg::launch(*reinterpret_cast<const tcg::Gemm*>(desc_host), reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
 
 extern "C" const char* pasn_strerror(int status) {
@@ -214,8 +224,16 @@ extern "C" int pasn_occurrence_only(const void* feat, const pasn_weights* w, con
   if (faulted()) return PASN_ERR_FAULT;
   if (dims->N == 0) return PASN_OK;
   if (!feat || !workspace) return PASN_ERR_INVALID;
-  if (dims->path == PASN_PATH_TILED && !(tiled_supported(*dims) && packed)) return PASN_ERR_UNSUPPORTED;
-  if (dims->path == PASN_PATH_TILED)
+  int err;
+  int fam = resolve_family(*dims, &err);   // same family (and therefore the same packed weights) as pasn_head_forward
+  if (err) return err;
+  if (fam != FAM_GENERIC && packed == nullptr) {
+    if (dims->path != PASN_PATH_AUTO) return PASN_ERR_UNSUPPORTED;
+    fam = FAM_GENERIC;
+  }
+  if (fam == FAM_FUSED)
+    return sm100_occurrence_only(feat, *w, packed, *dims, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (fam == FAM_TILED)
     return tiled_occurrence_only(feat, *w, packed, *dims, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
   return generic_occurrence_only(feat, *w, *dims, occurrence_map, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -104,6 +104,8 @@ int sm100_pack_weights(const pasn_weights& w, const pasn_dims& d, void* packed, 
 int sm100_head_forward(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, float* logits,
                        float* sim, void* occ, float* feats, float* dist, const pasn_push_args* push, void* ws,
                        size_t ws_bytes, cudaStream_t st);
+int sm100_occurrence_only(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, void* occ, void* ws,
+                          size_t ws_bytes, cudaStream_t st);
 int sm100_last_error(const void* ws, const pasn_dims& d, cudaStream_t st);
 void sm100_set_trace(void* dev_buf);
 void sm100_set_k1_variant(int variant);

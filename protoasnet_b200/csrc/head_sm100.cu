@@ -607,6 +607,10 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return e ? atoi(e) : 1; }();
   static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 1; }();
   k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
+  static const int x_drain = [] { const char* e = getenv("PASN_X_DRAIN"); return e ? atoi(e) : 0; }();
+  k1.x_drain = x_drain;
+  static const int flush_sleep = [] { const char* e = getenv("PASN_FLUSH_SLEEP"); return e ? atoi(e) : 0; }();
+  k1.flush_sleep = flush_sleep;
   static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 0; }();
   k1.ready = ready;
   const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
@@ -624,6 +628,7 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   if (rc) return rc;
   main_kernel_end(st);
   count_launch();
+  if (logits == nullptr) return PASN_OK;   // occurrence map only (sm100_occurrence_only): the prototype kernel is not needed
 
   const PackedLayout PL = packed_layout(d.C);
   K2Params k2{};
@@ -679,6 +684,13 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
     if (rc2) return rc2;
   }
   return PASN_OK;
+}
+
+// compute_occurence_map (src/models/Video_XProtoNet.py:100-109) for the shapes the fused path takes: the token kernel alone
+// (it writes the map on its way; the pooled vectors it also produces stay in the workspace).
+int sm100_occurrence_only(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, void* occ, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
+  return sm100_head_forward(feat, w, packed, d, nullptr, nullptr, occ, nullptr, nullptr, nullptr, ws, ws_bytes, st);
 }
 
 // surfaced for tests / debugging: non-zero if a kernel hit its bounded-wait limit (protocol bug) on the last call

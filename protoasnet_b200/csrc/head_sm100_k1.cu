@@ -465,6 +465,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
     const uint32_t jobs_per_tile = (uint32_t)nkc * (two_phase ? 2u : 1u);
     const uint32_t njobs = (uint32_t)ntiles * jobs_per_tile;
     bool ok = true;
+    // Wait for the ring slot of job g.  If it is not free yet the ring is full and this warp is about to stall (typically
+    // while the tile's serial chain runs): everything still in flight is waited for and published first, so that the
+    // issuer finds all XSLOTS chunks ready when layer 1 of the next tile starts (published chunks normally trail the
+    // issued ones by XDEPTH - 1).  The decision is made by lane 0 and broadcast: the publish protocol is warp-collective.
+    auto slot_free_or_drain = [&](uint32_t g, uint32_t xs, uint32_t xph, uint32_t& pub) -> bool {
+      const uint32_t full = __shfl_sync(0xffffffffu, mbar_test_wait(&bars[B_XEMPTY + xs], xph ^ 1) ? 0u : 1u, 0);
+      if (full && p.x_drain) {
+        if (pub < g) {
+          cp_async_wait<0>();
+          while (pub < g) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_XFULL + (pub % XSLOTS)]);
+            ++pub;
+          }
+        }
+      }
+      return bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301);
+    };
     if (p.nsc) {
       // channels_last feature map [N][S][C]: a voxel's 64 channels of a chunk are 128 contiguous, 16-byte aligned bytes,
       // i.e. one row of the K-major SWIZZLE_128B operand image.  16-byte L1-bypassing cp.async: eight lanes per voxel row,
@@ -479,7 +498,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       const int sub = lane & 7, r4 = lane >> 3;
       for (uint32_t g = 0; g < njobs; ++g) {
         const uint32_t xs = g % XSLOTS, xph = (g / XSLOTS) & 1;
-        if (!(ok = bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301))) break;
+        if (!slot_free_or_drain(g, xs, xph, pub)) { ok = false; break; }
         const int tile = (int)(g / jobs_per_tile);
         const int kc = (int)((g - (uint32_t)tile * jobs_per_tile) % (uint32_t)nkc);
         const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
@@ -491,7 +510,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           cp_async_16(dst0 + off_kmajor_sw128(row, sub * 8), src0 + (size_t)(valid ? row : 0) * p.C, valid ? 16u : 0u);
         }
         cp_async_commit();
-        if (g >= XDEPTH - 1) {
+        if (pub + (XDEPTH - 1) <= g) {
           cp_async_wait<XDEPTH - 1>();
           publish();
         }
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       };
       for (uint32_t g = 0; g < njobs; ++g) {
         const uint32_t xs = g % XSLOTS, xph = (g / XSLOTS) & 1;
-        if (!(ok = bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301))) break;
+        if (!slot_free_or_drain(g, xs, xph, pub)) { ok = false; break; }
         const int tile = (int)(g / jobs_per_tile);
         const int kc = (int)((g - (uint32_t)tile * jobs_per_tile) % (uint32_t)nkc);
         const int t = tile * TILE_M + 4 * lane;
@@ -532,7 +551,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
             cp_async_8(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u);
         }
         cp_async_commit();
-        if (g >= XDEPTH - 1) {
+        if (pub + (XDEPTH - 1) <= g) {
           cp_async_wait<XDEPTH - 1>();
           publish();
         }
@@ -876,6 +895,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
                 *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
                 *reinterpret_cast<__nv_bfloat16*>(img + 65536 + off) = l;
               }
+              // the burst of 2*PP stores per thread competes with the feature gather of the next tile's first chunks
+              // for the load/store path; these warps have nothing to do until that tile's layer 1 is done, so pace it
+              if (p.flush_sleep && (j & 3) == 3) __nanosleep(p.flush_sleep);
             }
           } else {
             // K2's A operand MN-major (row = (clip,p) contiguous, k = d): this thread's PP values for its d are

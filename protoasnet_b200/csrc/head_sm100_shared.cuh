@@ -58,6 +58,8 @@ struct K1Params {
   int* ready;                  // [N] per-clip hand-off counter to the prototype kernel: +1 per epilogue warp that has stored
                                // its part of the clip's pooled vectors, +1 for the clip's Osum row (K1_READY_TARGET in total)
   int l2_hints;                // 1: pooled-vector images are stored evict_last, the feature map is read evict_first
+  int flush_sleep;             // ns slept after every fourth prototype row of a clip flush (0: none)
+  int x_drain;                 // 1: feature-gather warps publish everything in flight before they block on a full ring
 };
 
 struct Ctx {

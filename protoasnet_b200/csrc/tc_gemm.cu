@@ -9,8 +9,17 @@
 //               bias / rank-1 term / ReLU / abs, converts, and leaves the rows either through a private swizzled
 //               staging slab + TMA store (16-byte aligned outputs) or with plain stores (small unaligned outputs)
 //
+// PAIR = true runs the same roles on 2-CTA clusters (cta_group::2): a pair owns a 256 x bn tile, each CTA loads its 128
+// rows of A and bn/2 rows of B (TMA completions of both CTAs land on the leader's "full" barrier), one thread of the
+// leader issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM, tcgen05.commit multicasts the
+// "stage free" / "accumulator full" arrivals to both CTAs, and the non-leader's epilogue warps hand the accumulator back
+// with remote arrivals.  Per flop a pair pulls 2/3 of the bytes from L2 that two independent CTAs would (the chain's big
+// GEMMs are bound by the ~6300 B/clk L2 -> SM fabric, not by the tensor pipe: profiles/README.md).
+//
 // Every mbarrier wait is bounded: a protocol fault becomes an error code in *err, not a hung GPU.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "sm100_prims.cuh"
 #include "tc_gemm.cuh"
@@ -21,16 +30,19 @@ using namespace sm100;
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64, STAGES = 3, MAX_STAGES = 8;
+// the operand ring is 3 x 48 KB; a stage only takes what its tiles need (A 16 KB + 128 B per row of the B tile this CTA
+// loads), so narrower tiles and CTA pairs get a deeper ring out of the same bytes -- what matters is the number of bytes
+// in flight against the L2 round trip, not the stage count
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES_MAX = 256 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES_MAX;   // 48 KB
 constexpr int EPI_WARPS = 8, EPI_WARP0 = 4, THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr uint32_t SLAB_BYTES = 4096;                             // 32 rows x 128 bytes
 constexpr uint32_t SM_STG = STAGES * STAGE_BYTES;                 // 147456: staging slabs, 2 per epilogue warp
-constexpr uint32_t SM_VEC = SM_STG + EPI_WARPS * 2 * SLAB_BYTES;  // 212992: per-warp bias / colvec slices (2 x 64 floats)
-constexpr uint32_t SM_BAR = SM_VEC + EPI_WARPS * 512;             // 217088
-constexpr uint32_t SM_MISC = SM_BAR + 16 * 8;
+constexpr uint32_t SM_VEC = SM_STG + EPI_WARPS * 2 * SLAB_BYTES;  // 212992: per-warp bias / colvec slices (2 groups x 2 x 64 floats)
+constexpr uint32_t SM_BAR = SM_VEC + EPI_WARPS * 1024;            // 221184
+constexpr uint32_t SM_MISC = SM_BAR + 24 * 8;
 constexpr uint32_t SMEM_BYTES = SM_MISC + 64;
-enum { B_FULL = 0, B_EMPTY = STAGES, B_ACCFULL = 2 * STAGES, B_ACCEMPTY = 2 * STAGES + 2 };
+enum { B_FULL = 0, B_EMPTY = MAX_STAGES, B_ACCFULL = 2 * MAX_STAGES, B_ACCEMPTY = 2 * MAX_STAGES + 2 };
 
 struct alignas(64) KParams {
   CUtensorMap tmA, tmB, tmO[4];   // out0 (hi), out0 lo, out1 (hi), out1 lo
@@ -44,6 +56,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+// CTA-pair form: the completion bytes are counted on the barrier at the same offset in the leader (even) CTA of the pair
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar) & 0xFEFFFFFFu)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -73,13 +92,10 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, 
   return wait_slow(bar, parity, err, code);
 }
 
-__device__ __forceinline__ float tv(const Output& o, float v) { return o.absval ? fabsf(v) : v; }
-__device__ __forceinline__ float act_apply(float v, int act) {
-  return act == ACT_RELU ? fmaxf(v, 0.f) : (act == ACT_ABS ? fabsf(v) : v);
-}
 
 }  // namespace
 
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -90,64 +106,85 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (tid == 0) *reinterpret_cast<volatile int*>(kp.err) = 700;
     return;
   }
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_ACCFULL + i], 1); mbar_init(&bars[B_ACCEMPTY + i], EPI_WARPS); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_ACCFULL + i], 1); mbar_init(&bars[B_ACCEMPTY + i], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     fence_mbar_init();
     prefetch_tmap(&kp.tmA);
     prefetch_tmap(&kp.tmB);
   }
-  if (warp == 2) tmem_alloc(tmem_ptr_s, 512);
+  if (warp == 2) { if constexpr (PAIR) tmem_alloc2(tmem_ptr_s, 512); else tmem_alloc(tmem_ptr_s, 512); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrival / multicast commit
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t sbase = smem_u32(smem);
   const int bn = g.bn;
+  const int bnl = PAIR ? bn / 2 : bn;                           // rows of the B tile this CTA loads
   const int tiles_per_batch = kp.tiles_m * kp.tiles_n;
   const int ntiles = g.batch * tiles_per_batch;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent walk of this CTA / pair
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BMT = PAIR ? 2 * BM : BM;                                   // rows of a (pair) tile
+  const uint32_t stage_bytes = A_BYTES + (uint32_t)bnl * 128u;              // multiple of 1024: swizzle atoms stay aligned
+  const uint32_t nst_fit = (STAGES * STAGE_BYTES) / stage_bytes;
+  const uint32_t nst = nst_fit < (uint32_t)MAX_STAGES ? nst_fit : (uint32_t)MAX_STAGES;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t s = 0, ph = 0;
       bool ok = true;
-      const uint32_t stage_tx = A_BYTES + (uint32_t)bn * 128u;
-      for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x) {
+      const uint32_t stage_tx = (A_BYTES + (uint32_t)bnl * 128u) * (PAIR ? 2u : 1u);   // both CTAs' bytes land on the leader's barrier
+      auto tma_load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+        if constexpr (PAIR) tma_load_3d_2sm(dst, map, c0, c1, c2, bar);
+        else tma_load_3d(dst, map, c0, c1, c2, bar);
+      };
+      for (int t = tile0; t < ntiles && ok; t += tstep) {
         const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
-        const int m0 = (r / kp.tiles_n) * BM, n0 = (r % kp.tiles_n) * bn;
+        const int m0 = (r / kp.tiles_n) * BMT + (int)rank * BM, n0 = (r % kp.tiles_n) * bn + (int)rank * bnl;
         const bool split_k = g.k_rows_per_batch > 0;
         const int krow0 = split_k ? b * g.k_rows_per_batch : 0;
         for (int pass = 0; pass < g.npass && ok; ++pass) {
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_EMPTY + s], ph ^ 1, kp.err, 701))) break;
-            const uint32_t dst = sbase + s * STAGE_BYTES;
-            mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
+            const uint32_t dst = sbase + s * stage_bytes;
+            if (rank == 0) mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
             const int krow = krow0 + kb * BK;   // K coordinate of MN-major operands (rows)
             if (!g.a_mn_major) {
-              tma_load_3d(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
+              tma_load(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
             } else {
               for (int j = 0; j < 2; ++j)
-                tma_load_3d(dst + j * 8192, &kp.tmA, g.a_off[pass] + m0 + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
-                            &bars[B_FULL + s]);
+                tma_load(dst + j * 8192, &kp.tmA, g.a_off[pass] + m0 + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
+                         &bars[B_FULL + s]);
             }
             if (!g.b_mn_major) {
-              tma_load_3d(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
+              tma_load(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
             } else {
-              for (int j = 0; j < bn / 64; ++j)
-                tma_load_3d(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
-                            (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s]);
+              for (int j = 0; j < bnl / 64; ++j)
+                tma_load(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
+                         (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s]);
             }
-            s = s + 1 == STAGES ? 0 : s + 1;
+            s = s + 1 == nst ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
     if (elect_one()) {
-      const uint32_t id = make_idesc_16(BM, (uint32_t)bn, 1u, 1u, g.a_mn_major ? 1u : 0u, g.b_mn_major ? 1u : 0u);
+      const uint32_t id = make_idesc_16(BMT, (uint32_t)bn, 1u, 1u, g.a_mn_major ? 1u : 0u, g.b_mn_major ? 1u : 0u);
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t acc) {
+        if constexpr (PAIR) mma_ss2_x(d, alo, ahi, blo, bhi, id, acc);
+        else mma_ss_x(d, alo, ahi, blo, bhi, id, acc);
+      };
+      auto commit = [&](uint32_t bar_saddr) {
+        if constexpr (PAIR) mma_commit2_a(bar_saddr, (uint16_t)3);
+        else mma_commit_a(bar_saddr);
+      };
       const uint32_t a_lbo = g.a_mn_major ? 8192u : 16u, a_kstep = g.a_mn_major ? 128u : 2u;
       constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
       const uint32_t b_lbo = g.b_mn_major ? 8192u : 16u, b_kstep = g.b_mn_major ? 128u : 2u;
@@ -155,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       uint32_t s = 0, ph = 0;
       bool ok = true;
       int i = 0;
-      for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++i) {
+      for (int t = tile0; t < ntiles && ok; t += tstep, ++i) {
         const uint32_t buf = i & 1;
         if (!(ok = bwait(&bars[B_ACCEMPTY + buf], ((i >> 1) & 1) ^ 1, kp.err, 711))) break;
         tc_fence_after();
@@ -164,16 +201,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
             tc_fence_after();
-            const uint32_t sa = sbase + s * STAGE_BYTES;
+            const uint32_t sa = sbase + s * stage_bytes;
             const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + A_BYTES, b_lbo);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) mma_ss_x(d, alo + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, id, (pass | kb | k4) ? 1u : 0u);
-            mma_commit_a(bar0 + 8u * (B_EMPTY + s));
-            s = s + 1 == STAGES ? 0 : s + 1;
+            for (int k4 = 0; k4 < 4; ++k4) mma(d, alo + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, (pass | kb | k4) ? 1u : 0u);
+            commit(bar0 + 8u * (B_EMPTY + s));
+            s = s + 1 == nst ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
           }
         }
-        if (ok) mma_commit_a(bar0 + 8u * (B_ACCFULL + buf));
+        if (ok) commit(bar0 + 8u * (B_ACCFULL + buf));
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -181,7 +218,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const int w = warp - EPI_WARP0, q = w & 3, h = w >> 2;
     const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t slab0 = sbase + SM_STG + (uint32_t)w * 2u * SLAB_BYTES;
-    float* vecs = reinterpret_cast<float*>(smem + SM_VEC + w * 512);   // [0,64) bias slice, [64,128) colvec slice
+    float* vecs_w = reinterpret_cast<float*>(smem + SM_VEC + w * 1024);   // per group: [0,64) bias slice, [64,128) colvec slice
+    // The per-element work below is what bounds the wide, short-K GEMMs of the chain (8 warps share 4 issue slots: every
+    // instruction per accumulator element costs ~1/4 cycle per element of the tile), so everything that is uniform
+    // over the launch is decided by branches around the element loops, never by selects inside them.
+    const bool has_vec = g.bias != nullptr || (g.rowparts != nullptr && g.colvec != nullptr);
+    const bool has_aux = g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr;
     const int nh = bn >= 128 ? 2 : 1;            // column halves in use (a 64-wide tile is one 64-column group: half 0 only)
     const int half_cols = bn / nh;
     const int ngroups = half_cols / 64;
@@ -202,19 +244,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(tv(o, v[32 * bx + 4 * c])),
-                         "f"(tv(o, v[32 * bx + 4 * c + 1])), "f"(tv(o, v[32 * bx + 4 * c + 2])), "f"(tv(o, v[32 * bx + 4 * c + 3]))
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[32 * bx + 4 * c]),
+                         "f"(v[32 * bx + 4 * c + 1]), "f"(v[32 * bx + 4 * c + 2]), "f"(v[32 * bx + 4 * c + 3])
                          : "memory");
+          }
+        } else if (o.mode == OUT_BF16_HILO && bx == 1) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = v[8 * c + 2 * j], a1 = v[8 * c + 2 * j + 1];
+              pk[j] = pack_bf16x2(a0 - round_bf16(a0), a1 - round_bf16(a1));
+            }
+            const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           }
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a0 = tv(o, v[8 * c + 2 * j]), a1 = tv(o, v[8 * c + 2 * j + 1]);
-              pk[j] = (o.mode == OUT_BF16_HILO && bx == 1) ? pack_bf16x2(a0 - round_bf16(a0), a1 - round_bf16(a1)) : pack_bf16x2(a0, a1);
-            }
+            for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1]);
             const uint32_t a = rowaddr + (uint32_t)((c ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
           }
@@ -233,27 +284,37 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     auto store_direct = [&](const Output& o, const float (&v)[64], int col0, int row, int b, bool row_ok) {
       if (!row_ok) return;
       const int ncols = o.ncols ? o.ncols : g.N;
-      const long long base = (long long)b * o.bs + (long long)row * o.ld;
+      // row-major rows, or (trans_S) channel-major per clip with the token index running along the rows of this tile
+      const long long base = o.trans_S > 0 ? (long long)(row / o.trans_S) * o.bs + (row % o.trans_S)
+                                           : (long long)b * o.bs + (long long)row * o.ld;
+      const long long cstep = o.trans_S > 0 ? o.ld : 1;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const int col = col0 + j;
         if (col >= ncols) continue;
-        const float x = tv(o, v[j]);
+        const float x = v[j];
         if (o.mode == OUT_F32) {
-          reinterpret_cast<float*>(o.ptr)[base + col] = x;
+          reinterpret_cast<float*>(o.ptr)[base + col * cstep] = x;
         } else {
           __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
           const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-          p16[base + col] = hi;
-          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
+          p16[base + col * cstep] = hi;
+          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col * cstep] = __float2bfloat16_rn(x - __bfloat162float(hi));
         }
       }
     };
 
-    for (int t = blockIdx.x; t < ntiles && ok; t += gridDim.x, ++i) {
+    // hand an accumulator buffer back to the MMA issuer (of the leader CTA)
+    auto acc_release = [&](uint32_t buf) {
+      if constexpr (PAIR) {
+        if (rank != 0) { mbar_arrive_cluster(mapa_u32(smem_u32(&bars[B_ACCEMPTY + buf]), 0)); return; }
+      }
+      mbar_arrive(&bars[B_ACCEMPTY + buf]);
+    };
+    for (int t = tile0; t < ntiles && ok; t += tstep, ++i) {
       const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
       const int tn = r % kp.tiles_n;
-      const int m0 = (r / kp.tiles_n) * BM, n0 = tn * bn;
+      const int m0 = (r / kp.tiles_n) * BMT + (int)rank * BM, n0 = tn * bn;
       const uint32_t buf = i & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -263,25 +324,31 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         for (int j = 0; j < g.nparts; ++j) rowterm += rp[j];
       }
       float psum = 0.f;
+      if (has_vec && h < nh) {   // bias / colvec slices of this warp's groups -> per-warp smem, before the accumulator is due
+        __syncwarp();
+        for (int cg = 0; cg < ngroups; ++cg) {
+          const int colb = n0 + h * half_cols + 64 * cg;
+          float* vecs = vecs_w + 128 * cg;
+          for (int j = lane; j < 64; j += 32) {
+            const int col = colb + j;
+            vecs[j] = (g.bias != nullptr && col < g.N) ? g.bias[col] : 0.f;
+            vecs[64 + j] = (g.colvec != nullptr && col < g.N) ? g.colvec[col] : 0.f;
+          }
+        }
+        __syncwarp();
+      }
       if (!(ok = bwait(&bars[B_ACCFULL + buf], (i >> 1) & 1, kp.err, 721))) break;
       tc_fence_after();
       if (h >= nh) {   // nothing to read for this warp: release the accumulator, keep the psum table dense
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+        if (lane == 0) acc_release(buf);
         if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = 0.f;
         continue;
       }
       for (int cg = 0; cg < ngroups; ++cg) {
         const int cl = h * half_cols + 64 * cg;       // column inside the tile
         const int col0 = n0 + cl;
-        // bias / colvec slices of this group -> per-warp smem (broadcast reads below)
-        __syncwarp();
-        for (int j = lane; j < 64; j += 32) {
-          const int col = col0 + j;
-          vecs[j] = (g.bias != nullptr && col < g.N) ? g.bias[col] : 0.f;
-          vecs[64 + j] = (g.colvec != nullptr && col < g.N) ? g.colvec[col] : 0.f;
-        }
-        __syncwarp();
+        const float* vecs = vecs_w + 128 * cg;
         float v[64];
         {
           uint32_t ra[32], rb[32];
@@ -294,43 +361,67 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         if (cg == ngroups - 1) {   // all TMEM reads of this tile are done: hand the accumulator back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY + buf]);
+          if (lane == 0) acc_release(buf);
         }
+        if (has_vec) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          const float4 bb = *reinterpret_cast<const float4*>(vecs + 4 * j4);
-          const float4 cc = *reinterpret_cast<const float4*>(vecs + 64 + 4 * j4);
-          v[4 * j4 + 0] = act_apply(fmaf(rowterm, cc.x, v[4 * j4 + 0] + bb.x), g.act);
-          v[4 * j4 + 1] = act_apply(fmaf(rowterm, cc.y, v[4 * j4 + 1] + bb.y), g.act);
-          v[4 * j4 + 2] = act_apply(fmaf(rowterm, cc.z, v[4 * j4 + 2] + bb.z), g.act);
-          v[4 * j4 + 3] = act_apply(fmaf(rowterm, cc.w, v[4 * j4 + 3] + bb.w), g.act);
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(vecs + 4 * j4);
+            const float4 cc = *reinterpret_cast<const float4*>(vecs + 64 + 4 * j4);
+            v[4 * j4 + 0] = fmaf(rowterm, cc.x, v[4 * j4 + 0] + bb.x);
+            v[4 * j4 + 1] = fmaf(rowterm, cc.y, v[4 * j4 + 1] + bb.y);
+            v[4 * j4 + 2] = fmaf(rowterm, cc.z, v[4 * j4 + 2] + bb.z);
+            v[4 * j4 + 3] = fmaf(rowterm, cc.w, v[4 * j4 + 3] + bb.w);
+          }
         }
-        if (g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr) {
+        if (g.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (g.act == ACT_ABS) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fabsf(v[j]);
+        }
+        if (has_aux) {
           // element-wise epilogue inputs (backward: + upstream gradient, * sign of the |.| argument, ReLU mask)
           if (row_ok) {
             const float* ad = g.addin.ptr ? reinterpret_cast<const float*>(g.addin.ptr) + (long long)b * g.addin.bs + (long long)row * g.addin.ld : nullptr;
             const __nv_bfloat16* sg = g.signin.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.signin.ptr) + (long long)b * g.signin.bs + (long long)row * g.signin.ld : nullptr;
             const __nv_bfloat16* mk = g.mask.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.mask.ptr) + (long long)b * g.mask.bs + (long long)row * g.mask.ld : nullptr;
+            const long long acs = g.addin.cs ? g.addin.cs : 1, scs = g.signin.cs ? g.signin.cs : 1, mcs = g.mask.cs ? g.mask.cs : 1;
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
               const int col = col0 + j;
               if (col < g.N) {
-                if (ad) v[j] += __ldg(ad + col);
-                if (sg) { const float x = __bfloat162float(sg[col]); v[j] = x > 0.f ? v[j] : (x < 0.f ? -v[j] : 0.f); }
-                if (mk) v[j] = __bfloat162float(mk[col]) > 0.f ? v[j] : 0.f;
+                if (ad) v[j] += __ldg(ad + col * acs);
+                if (sg) { const float x = __bfloat162float(sg[col * scs]); v[j] = x > 0.f ? v[j] : (x < 0.f ? -v[j] : 0.f); }
+                if (mk) v[j] = __bfloat162float(mk[col * mcs]) > 0.f ? v[j] : 0.f;
               }
             }
           }
         }
         if (g.psum != nullptr) {
-          const bool rounded = g.psum_rounded != 0;
+          if (col0 + 64 <= g.N) {
+            if (g.psum_rounded) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) psum += (col0 + j < g.N) ? (rounded ? round_bf16(v[j]) : v[j]) : 0.f;
+              for (int j = 0; j < 64; ++j) psum += round_bf16(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) psum += v[j];
+            }
+          } else {
+            const bool rounded = g.psum_rounded != 0;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) psum += (col0 + j < g.N) ? (rounded ? round_bf16(v[j]) : v[j]) : 0.f;
+          }
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           const Output& o = g.out[mi];
           if (o.mode == OUT_NONE) continue;
+          if (o.absval) {   // |value| next to an output that keeps the sign: only the first output may be the signed one
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fabsf(v[j]);
+          }
           if (kp.out_tma[mi]) store_tma(o, mi, v, col0, m0 + q * 32, b);
           else store_direct(o, v, col0, row, b, row_ok);
         }
@@ -342,7 +433,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tbase, 512);
+  if constexpr (PAIR) cluster_sync_all();   // the partner may still read this CTA's shared memory / signal its barriers
+  if (warp == 2) { if constexpr (PAIR) tmem_dealloc2(tbase, 512); else tmem_dealloc(tbase, 512); }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -393,16 +485,19 @@ int launch(const Gemm& g, cudaStream_t st) {
   if (g.npass < 1 || g.npass > 4 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return PASN_ERR_CUDA;
     attr_done = true;
   }
+  static const int pair_env = [] { const char* e = getenv("PASN_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // A/B switch
+  const bool pair = (pair_env >= 0 ? pair_env != 0 : g.pair != 0) && g.bn >= 128 && g.M > BM;
   int* fault = fault_word();   // bounded waits report into the host-mapped sticky fault word
   if (fault == nullptr) return PASN_ERR_CUDA;
   KParams kp;
   kp.g = g;
   kp.err = fault;
-  kp.tiles_m = ceil_div(g.M, BM);
+  kp.tiles_m = ceil_div(g.M, pair ? 2 * BM : BM);
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);
   const bool split_k = g.k_rows_per_batch > 0;
@@ -419,7 +514,7 @@ int launch(const Gemm& g, cudaStream_t st) {
   }
   if (!g.b_mn_major) {
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
-                  (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)g.bn))
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)(pair ? g.bn / 2 : g.bn)))
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
@@ -431,7 +526,7 @@ int launch(const Gemm& g, cudaStream_t st) {
     kp.out_tma[mi] = 0;
     kp.tmO[2 * mi] = kp.tmA;
     kp.tmO[2 * mi + 1] = kp.tmA;
-    if (o.mode == OUT_NONE || !out_aligned(o)) continue;
+    if (o.mode == OUT_NONE || o.trans_S > 0 || !out_aligned(o)) continue;
     const bool f32 = o.mode == OUT_F32;
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int elt = f32 ? 4 : 2;
@@ -450,8 +545,19 @@ int launch(const Gemm& g, cudaStream_t st) {
     return n;
   }();
   const long long ntiles = (long long)g.batch * kp.tiles_m * kp.tiles_n;
-  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-  tc_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(kp);
+  if (!pair) {
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    tc_gemm_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(kp);
+  } else {
+    const int npairs = (int)(ntiles < num_sms / 2 ? ntiles : num_sms / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, kp) != cudaSuccess) return PASN_ERR_CUDA;
+  }
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;

@@ -23,13 +23,16 @@ struct Output {
   long long ld, bs;   // row / batch stride in elements
   int lo_off;         // OUT_BF16_HILO: column offset of the lo half (the hi half starts at column 0)
   int ncols;          // columns of this output (0: N); columns beyond it are computed but not stored
-  int absval;         // store |value| (the other output keeps the signed value)
+  int absval;         // store |value| (only on the LAST output in use: the values are made absolute in place)
+  int trans_S;        // > 0: rows are tokens (clip = m / trans_S, voxel = m % trans_S) and the output is channel-major per clip,
+                      // element (m, n) at ptr + (m / trans_S) * bs + n * ld + m % trans_S  (plain stores, coalesced along m)
 };
 
-// optional element-wise epilogue input with the indexing of an output: element (b, m, n) at ptr[b*bs + m*ld + n]
+// optional element-wise epilogue input: element (b, m, n) at ptr[b*bs + m*ld + n*cs]  (cs = 0 means 1; cs > 1 with
+// ld = 1 reads a transposed array, coalesced along m)
 struct Aux {
   const void* ptr;
-  long long ld, bs;
+  long long ld, bs, cs;
 };
 
 struct Gemm {
@@ -53,6 +56,8 @@ struct Gemm {
   Output out[2];
   float* psum;                   // optional [batch*M][2*tiles_n]: row sums of the outputs per column half-tile ...
   int psum_rounded;              // ... of the bf16-rounded values (what a bf16 consumer of out[0] will read) or of the fp32 values
+  int pair;                      // 1: CTA pairs (cta_group::2): 256 x bn tiles, each CTA of a 2-CTA cluster loads its 128 rows of A
+                                 // and half of the B tile -- a third less L2 -> SM traffic per flop (bn >= 128 only; else ignored)
 };
 
 int launch(const Gemm& g, cudaStream_t st);   // 0 or a negative pasn_status

@@ -138,6 +138,7 @@ __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long 
 
 // passes of a product of two operands that each come as planes (hi at column 0, lo at column *_lo)
 void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo) {
+  g.pair = 1;   // CTA pairs wherever the shape allows (tc_gemm.cu decides)
   for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = 0;
   if (ex == 1) { g.npass = 1; return; }
   // hi*hi, hi*lo, lo*hi.  The lo*lo term is below the representation error of the split itself (each operand keeps 16

@@ -143,20 +143,18 @@ class _HeadRuntime:
         return {"logits": logits, "similarity": sim, "occurrence_map": occ, "features_extracted": feats, "distance": dist}
 
     def occurrence_only(self, x: torch.Tensor) -> torch.Tensor:
-        """compute_occurence_map: the occurrence branch alone, on the tiled tensor-core path when the shape qualifies."""
+        """compute_occurence_map: served by the kernel family forward() uses for this shape (fused token kernel alone, the
+        occurrence branch of the tiled chain, or the generic path)."""
         lib = _lib.load()
         m = self.owner
-        path = m.kernel_path if m.kernel_path == _lib.PASN_PATH_GENERIC else _lib.PASN_PATH_TILED
-        dims, x, spatial = self.make_dims(x, path)
-        if path == _lib.PASN_PATH_TILED and not lib.pasn_tcgen05_supported(C.byref(dims)):
-            dims.path = _lib.PASN_PATH_GENERIC
+        dims, x, spatial = self.make_dims(x, m.kernel_path)
         dev = x.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             w, tensors = self._weights_struct(m)
             occ = torch.empty((dims.N, dims.P, 1) + spatial, dtype=x.dtype, device=dev)
             if dims.N > 0:
-                packed = self._packed_weights(lib, dims, w, tensors, dev, stream) if dims.path == _lib.PASN_PATH_TILED else None
+                packed = self._packed_weights(lib, dims, w, tensors, dev, stream) if dims.path != _lib.PASN_PATH_GENERIC else None
                 ws = self._workspace(lib, dims, dev)
                 _lib.check(lib.pasn_occurrence_only(x.data_ptr(), C.byref(w), _ptr(packed), C.byref(dims), occ.data_ptr(),
                                                     ws.data_ptr(), ws.numel(), stream), "pasn_occurrence_only")
