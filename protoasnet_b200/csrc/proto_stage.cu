@@ -19,6 +19,65 @@ constexpr int PS_WARPS = PS_THREADS / 32;
 
 // One warp per (clip, prototype) row: cosine vs the prototype vector, (cos+1)/2, 1-s, push key.  Rows are spread over
 // the whole grid (N*P rows / 8 per block), so P = 40 and P = 4096 both fill the machine.
+// The warp stride over the rows is a multiple of P, so a warp keeps ONE prototype: its vector, already divided by its
+// clamped norm, lives in registers (NV = D / 32 values per lane), and a feature row is read from memory exactly once
+// (NV independent coalesced loads in flight).  Element -> lane mapping and the order of every sum are those of the
+// generic loop below (d = lane + 32 i), so both forms give the same bits.
+template <int NV>
+__global__ void __launch_bounds__(256) proto_rows_reg_kernel(
+    const float* __restrict__ feats, const float* __restrict__ protos, long long rows, int P,
+    float* __restrict__ sim, float* __restrict__ dist, const int64_t* __restrict__ labels,
+    const int32_t* __restrict__ proto_class, long long global_offset, unsigned long long* __restrict__ best_key) {
+  constexpr int D = NV * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * 8 + warp, wstride = (long long)gridDim.x * 8;   // wstride % P == 0 (host)
+  if (w0 >= rows) return;
+  const int p = (int)(w0 % P);
+  float vq[NV];
+  {
+    const float* v = protos + (size_t)p * D;
+    float vv = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { vq[i] = v[lane + 32 * i]; vv = fmaf(vq[i], vq[i], vv); }
+    vv = warp_sum(vv);
+    const float nv = fmaxf(sqrtf(vv), 1e-8f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vq[i] = vq[i] / nv;
+  }
+  const int pc = best_key != nullptr ? proto_class[p] : 0;
+  for (long long r = w0; r < rows; r += wstride) {
+    const float* f = feats + (size_t)r * D;
+    float a[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) a[i] = __ldcs(f + lane + 32 * i);
+    float ff = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ff = fmaf(a[i], a[i], ff);
+    ff = warp_sum(ff);
+    const float nf = fmaxf(sqrtf(ff), 1e-8f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dot = fmaf(a[i] / nf, vq[i], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      const long long n = r / P;
+      const float s = (dot + 1.0f) / 2.0f;
+      const float dd = 1.0f - s;
+      sim[r] = s;
+      if (dist) dist[r] = dd;
+      if (best_key != nullptr) {
+        if (pc < 0 || (long long)pc == labels[n]) {
+          const unsigned long long key = pack_key(dd, (uint32_t)(global_offset + n));
+          // plain read as a filter (the value only ever decreases), atomic only for candidates
+          if ((long long)(key ^ PASN_KEY_SIGN) < *reinterpret_cast<volatile long long*>(best_key + p))
+            key_atomic_min_global(&best_key[p], key);
+        }
+      }
+    }
+  }
+}
+
+// any D: the same arithmetic with the row read twice
 __global__ void __launch_bounds__(PS_THREADS) proto_rows_kernel(
     const float* __restrict__ feats, const float* __restrict__ protos, long long rows, int P, int D,
     float* __restrict__ sim, float* __restrict__ dist, const int64_t* __restrict__ labels,
@@ -74,6 +133,26 @@ __global__ void __launch_bounds__(PS_THREADS) proto_logits_kernel(const float* _
     }
   }
 }
+// thousands of prototypes, few clips: one block per (clip, class) pair
+__global__ void __launch_bounds__(PS_THREADS) proto_logits_wide_kernel(const float* __restrict__ sim,
+                                                                       const float* __restrict__ last_layer, int N, int P, int K,
+                                                                       float* __restrict__ logits) {
+  __shared__ float red[PS_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / K, k = blockIdx.x - n * K;
+  const float* s = sim + (size_t)n * P;
+  const float* wl = last_layer + (size_t)k * P;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < P; p += PS_THREADS) acc = fmaf(s[p], wl[p], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < PS_WARPS; ++i) t += red[i];
+    logits[(size_t)n * K + k] = t;
+  }
+}
 
 // best_vec[p,:] = feats[n*,p,:] where n* = clip of this call that holds best_key[p] (keys carry the global clip index);
 // prototypes whose best clip lies outside [offset, offset+N) keep their row.  One block per prototype.
@@ -92,14 +171,34 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
                        float* logits, float* sim, float* dist, const pasn_push_args* push, cudaStream_t st) {
   if (N <= 0) return PASN_OK;
   const long long rows = (long long)N * P;
-  long long blocks = (rows + PS_WARPS - 1) / PS_WARPS;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  proto_rows_kernel<<<(unsigned)blocks, PS_THREADS, 0, st>>>(
-      feats, protos, rows, P, D, sim, dist, push ? push->labels : nullptr, push ? push->proto_class : nullptr,
-      push ? (long long)push->global_offset : 0, push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr);
+  const int64_t* labels = push ? push->labels : nullptr;
+  const int32_t* pcls = push ? push->proto_class : nullptr;
+  const long long goff = push ? (long long)push->global_offset : 0;
+  unsigned long long* bkey = push ? reinterpret_cast<unsigned long long*>(push->best_key) : nullptr;
+  if (D == 128 || D == 256 || D == 512 || D == 1024) {
+    // warps = P * m (so a warp keeps its prototype), 8 warps per block: blocks * 8 must be a multiple of P
+    long long per = P;                                   // warps per "round" of all prototypes
+    long long m = (148LL * 32 * 8 + per - 1) / per;      // rounds wanted to fill the machine
+    if (m > N) m = N;
+    if (m < 1) m = 1;
+    long long warps = per * m;
+    while (warps % 8 != 0) warps += per;                 // at most 7 steps; stays a multiple of P
+    const unsigned blocks = (unsigned)(warps / 8);
+    if (D == 128) proto_rows_reg_kernel<4><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else if (D == 256) proto_rows_reg_kernel<8><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else if (D == 512) proto_rows_reg_kernel<16><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else proto_rows_reg_kernel<32><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+  } else {
+    long long blocks = (rows + PS_WARPS - 1) / PS_WARPS;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    proto_rows_kernel<<<(unsigned)blocks, PS_THREADS, 0, st>>>(feats, protos, rows, P, D, sim, dist, labels, pcls, goff, bkey);
+  }
   PASN_LAUNCH_CHECK();
   count_launch();
-  proto_logits_kernel<<<N < 148 * 8 ? N : 148 * 8, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
+  if (P >= 1024 && (long long)N * K <= 148 * 64)
+    proto_logits_wide_kernel<<<N * K, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
+  else
+    proto_logits_kernel<<<N < 148 * 8 ? N : 148 * 8, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
   PASN_LAUNCH_CHECK();
   count_launch();
   if (push && push->best_vec) {   // winner capture in the same pass (push_abs_revision.py:299-302)

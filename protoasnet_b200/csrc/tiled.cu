@@ -26,6 +26,8 @@ struct Plan {
   int C, D, D2, P, K, S, Sp;   // Sp: column pitch of one plane of the pooling A operand (occurrence values)
   bool occ_direct;             // bf16 mode and 16-byte aligned rows: the pooling reads the occurrence_map buffer itself
   bool w2_first;               // F = W2 H1 + b2 before the pooling (cheaper when S is small against P)
+  bool tok_c;                  // few prototypes: O over all tokens at once (token-major), the map leaves channel-major per clip
+  int Pp;                      // column pitch of one plane of the token-major occurrence values
   int bn_c, tiles_n_c;         // tile width / count along S of the O GEMM (psum parts = 2 * tiles_n_c)
   int nb;                      // clips per chunk
   size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, total;
@@ -41,11 +43,14 @@ Plan make_plan(const pasn_dims& d) {
   // MACs of the W2 stage per clip: S*D*D*passes before the pooling, P*D*D*passes after it (bf16 mode: the pooled vectors
   // go in as hi + lo planes, two passes; fp32 mode: three passes either way)
   p.w2_first = p.ex == 1 ? (d.S < 2 * d.P) : (d.S < d.P);
+  p.tok_c = d.P <= 64;         // (the full chain uses it only together with w2_first: the other order needs row sums over s)
+  p.Pp = (d.P + 7) / 8 * 8;
   p.Sp = p.ex == 2 ? (d.S + 63) / 64 * 64 : (d.S + 7) / 8 * 8;
   p.bn_c = pick_bn(p.ex == 2 ? p.Sp : d.S);
   p.tiles_n_c = ceil_div(p.ex == 2 ? p.Sp : d.S, p.bn_c);
   const size_t S = d.S, ex = p.ex;
-  const size_t per_clip = S * ex * d.C * 2 + S * ex * 2 * d.D * 2 + S * ex * p.D2 * 2 + (size_t)d.P * ex * p.Sp * 2 +
+  const size_t occ_elems = (size_t)d.P * p.Sp > S * p.Pp ? (size_t)d.P * p.Sp : S * p.Pp;   // either orientation
+  const size_t per_clip = S * ex * d.C * 2 + S * ex * 2 * d.D * 2 + S * ex * p.D2 * 2 + occ_elems * ex * 2 +
                           (size_t)d.P * 2 * p.tiles_n_c * 4 + (size_t)d.P * 2 * d.D * 2 + S * ex * d.D * 2 +
                           (size_t)d.P * d.D * 4 + 2048;
   long long nb = (long long)(((size_t)2 << 30) / per_clip);
@@ -57,7 +62,7 @@ Plan make_plan(const pasn_dims& d) {
   p.off_xt = take((size_t)p.nb * S * ex * d.C * 2);
   p.off_y = take((size_t)p.nb * S * ex * 2 * d.D * 2);
   p.off_g2 = take((size_t)p.nb * S * ex * p.D2 * 2);
-  p.off_occ = take((size_t)p.nb * d.P * ex * p.Sp * 2);
+  p.off_occ = take((size_t)p.nb * occ_elems * ex * 2);
   p.off_psum = take((size_t)p.nb * d.P * 2 * p.tiles_n_c * 4);
   p.off_pool = take(p.w2_first ? 0 : (size_t)p.nb * d.P * 2 * d.D * 2);
   p.off_f = take(p.w2_first ? (size_t)p.nb * S * ex * d.D * 2 : 0);
@@ -102,25 +107,33 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int n, int round, 
 }
 
 // feature map -> token-major bf16 planes XT[(n*S + s)][ex*C]
-//   NCS ([n][C][S]): 32x32 tile transpose through shared memory;  NSC fp32 ([n][S][C]): plane split only
+//   NCS ([n][C][S]): 64-channel x 32-voxel tiles through shared memory: loads run along s (one channel row segment per warp
+//   instruction), stores along c (one full 128-byte line of bf16 channel pairs per token and plane);
+//   NSC fp32 ([n][S][C]): plane split only
 template <typename T>
-__global__ void to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int ex, __nv_bfloat16* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.z, c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+__global__ void __launch_bounds__(256) to_tokens_ncs_kernel(const T* __restrict__ x, int C, int S, int ex, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, s0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* xn = x + (size_t)n * C * S;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, s = s0 + threadIdx.x;
-    tile[j][threadIdx.x] = (c < C && s < S) ? to_f32<T>(xn[(size_t)c * S + s]) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cl = warp * 8 + j, c = c0 + cl, s = s0 + lane;
+    tile[cl][lane] = (c < C && s < S) ? to_f32<T>(xn[(size_t)c * S + s]) : 0.f;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int s = s0 + j, c = c0 + threadIdx.x;
+  const int c = c0 + 2 * lane;           // C is a multiple of 64 on this path
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int sl = warp * 4 + j, s = s0 + sl;
     if (s < S && c < C) {
-      const float v = tile[threadIdx.x][j];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float v0 = tile[2 * lane][sl], v1 = tile[2 * lane + 1][sl];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
       __nv_bfloat16* row = out + ((size_t)n * S + s) * ex * C;
-      row[c] = hi;
-      if (ex == 2) *(row + C + c) = __float2bfloat16_rn(v - __bfloat162float(hi));
+      *reinterpret_cast<__nv_bfloat162*>(row + c) = __nv_bfloat162(h0, h1);
+      if (ex == 2)
+        *reinterpret_cast<__nv_bfloat162*>(row + C + c) =
+            __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
     }
   }
 }
@@ -199,17 +212,22 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   // ---- tokens
   const __nv_bfloat16* xt;
   const char* x = reinterpret_cast<const char*>(feat) + (size_t)n0 * C * S * elt;
+  // bf16 NCDHW feature maps with 16-byte aligned channel rows need no transposition: [C][S] per clip IS the MN-major form
+  // of the A operand (voxels contiguous), which the TMA unit tiles straight out of the caller's buffer
+  const bool x_direct = d.layout == PASN_LAYOUT_NCS && ex == 1 && (S * 2) % 16 == 0 && ((uintptr_t)x & 15) == 0;
   if (d.layout == PASN_LAYOUT_NSC && ex == 1) {
     xt = reinterpret_cast<const __nv_bfloat16*>(x);   // channels_last bf16 feature map: already token-major
     if (((uintptr_t)xt & 15) != 0) return PASN_ERR_ALIGN;
+  } else if (x_direct) {
+    xt = reinterpret_cast<const __nv_bfloat16*>(x);
   } else {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ws + p.off_xt);
     if (d.layout == PASN_LAYOUT_NSC) {
       to_tokens_nsc_f32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, C, dst);
     } else {
-      dim3 grid(ceil_div(S, 32), ceil_div(C, 32), nb), block(32, 8);
-      if (ex == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, dst);
-      else to_tokens_ncs_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, dst);
+      dim3 grid(ceil_div(S, 32), ceil_div(C, 64), nb);
+      if (ex == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, dst);
+      else to_tokens_ncs_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, dst);
     }
     PASN_LAUNCH_CHECK();
     count_launch();
@@ -239,6 +257,11 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     set_passes(g, ex, C, C);
     g.bias = occ_only ? b13 + D : b13; g.act = tcg::ACT_RELU;
     g.out[0] = {Y, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_BF16_HILO, (long long)ex * nA, 0, nA};
+    if (x_direct) {   // one GEMM per clip: rows = its S voxels, operand [C rows][S] as it lies in the feature map
+      g.a_mn_major = 1; g.lda = S; g.a_bs = (long long)C * S; g.a_batched = 1; g.ka = S; g.a_rows = C;
+      g.M = S; g.batch = nb;
+      g.out[0].bs = (long long)S * ex * nA;
+    }
     if ((rc = tcg::launch(g, st))) return rc;
   }
   // ---- (B) G2 = relu(G1 W4^T + b4)
@@ -257,7 +280,29 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   void* occ_user = occ ? reinterpret_cast<char*>(occ) + (size_t)n0 * P * S * elt : nullptr;
   const __nv_bfloat16* pool_a = nullptr;     // pooling A operand
   long long pool_lda = 0;
-  {
+  const bool tok_c = p.tok_c && (occ_only || p.w2_first);
+  if (tok_c) {
+    // few prototypes: O^T = |G2 W5^T| over all tokens in one GEMM (rows = tokens, N = P).  The occurrence map leaves
+    // channel-major per clip through plain stores that are coalesced along the voxels; the token-major copy
+    // [T][ex*Pp] is the pooling's MN-major A operand.
+    tcg::Gemm g{};
+    g.A = G2; g.lda = (long long)ex * D2; g.a_batched = 0; g.ka = ex * D2;
+    g.B = W5; g.ldb = (long long)ex * D2; g.b_batched = 0; g.kb = ex * D2;
+    g.M = (int)T; g.N = P; g.K = D2; g.batch = 1; g.bn = 64;
+    set_passes(g, ex, D2, D2);
+    g.act = tcg::ACT_ABS;
+    int no = 0;
+    if (occ_user != nullptr) {
+      g.out[no] = {occ_user, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_F32, (long long)S, (long long)P * S, 0, P, 0, S};
+      ++no;
+    }
+    if (!occ_only) {
+      g.out[no] = {OCC, ex == 1 ? tcg::OUT_BF16 : tcg::OUT_BF16_HILO, (long long)ex * p.Pp, 0, p.Pp, P, 0, 0};
+      ++no;
+      pool_a = OCC; pool_lda = (long long)ex * p.Pp;
+    }
+    if ((rc = tcg::launch(g, st))) return rc;
+  } else {
     tcg::Gemm g{};
     g.A = W5; g.lda = (long long)ex * D2; g.a_batched = 0; g.ka = ex * D2;
     g.B = G2; g.ldb = (long long)ex * D2; g.b_bs = (long long)S * ex * D2; g.b_batched = 1; g.kb = ex * D2;
@@ -307,6 +352,10 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       g.b_mn_major = 1; g.b_rows = S;
       g.M = P; g.N = D; g.K = ex == 2 ? p.Sp : S; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
       set_passes(g, ex, p.Sp, D);
+      if (tok_c) {   // occurrence values token-major: [S rows][P] per clip, prototypes contiguous (MN-major A)
+        g.a_mn_major = 1; g.a_bs = (long long)S * pool_lda; g.ka = ex * p.Pp; g.a_rows = S; g.K = S;
+        set_passes(g, ex, p.Pp, D);
+      }
       g.act = tcg::ACT_NONE;
       g.out[0] = {FE, tcg::OUT_F32, (long long)D, (long long)P * D, 0};
       if ((rc = tcg::launch(g, st))) return rc;
