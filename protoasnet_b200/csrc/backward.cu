@@ -225,11 +225,15 @@ int bwd_chunk(const pasn_dims& d) {
 
 }  // namespace
 
-size_t backward_workspace_bytes(const pasn_dims& d) { return align_up(per_clip_floats(d) * 4 * bwd_chunk(d), 256) + 256; }
+size_t backward_workspace_bytes(const pasn_dims& d) {
+  if (tiled_backward_supported(d)) return tiled_backward_workspace_bytes(d);
+  return align_up(per_clip_floats(d) * 4 * bwd_chunk(d), 256) + 256;
+}
 
 int head_backward(const void* feat, const pasn_weights& w, const pasn_dims& d, const float* gLogits, const float* gSim,
                   const float* gOcc, const pasn_grads& g, float* gX, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (d.D % 2 != 0) return PASN_ERR_UNSUPPORTED;
+  if (tiled_backward_supported(d)) return tiled_head_backward(feat, w, d, gLogits, gSim, gOcc, g, gX, ws, ws_bytes, st);
   if (ws_bytes < backward_workspace_bytes(d)) return PASN_ERR_WORKSPACE;
   const int nbm = bwd_chunk(d);
   const int D = d.D, D2 = d.D / 2, S = d.S, P = d.P, C = d.C, K = d.K;

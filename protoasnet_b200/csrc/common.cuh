@@ -96,6 +96,13 @@ int tiled_head_forward(const void* feat, const pasn_weights& w, const void* pack
 int tiled_occurrence_only(const void* feat, const pasn_weights& w, const void* packed, const pasn_dims& d, void* occ, void* ws,
                           size_t ws_bytes, cudaStream_t st);
 
+// backward on the tensor cores (tiled.cu): fp32-grade hi/lo GEMM chain; serves the shapes tiled_supported() takes unless
+// dims.path asks for the generic CUDA-core kernels
+bool tiled_backward_supported(const pasn_dims& d);
+size_t tiled_backward_workspace_bytes(const pasn_dims& d);
+int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims& d, const float* gLogits, const float* gSim,
+                        const float* gOcc, const pasn_grads& g, float* gX, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- fused tcgen05 path (head_sm100.cu) -----------------------------------------------------
 bool sm100_supported(const pasn_dims& d);
 size_t sm100_workspace_bytes(const pasn_dims& d);

@@ -178,7 +178,8 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
   if (D == 128 || D == 256 || D == 512 || D == 1024) {
     // warps = P * m (so a warp keeps its prototype), 8 warps per block: blocks * 8 must be a multiple of P
     long long per = P;                                   // warps per "round" of all prototypes
-    long long m = (148LL * 32 * 8 + per - 1) / per;      // rounds wanted to fill the machine
+    long long m = (148LL * 4 * 8 + per - 1) / per;       // rounds wanted: ~4 blocks per SM, several rows per warp so that
+                                                         // the prototype set-up (load, norm, NV divisions) is amortised
     if (m > N) m = N;
     if (m < 1) m = 1;
     long long warps = per * m;

@@ -429,4 +429,417 @@ int tiled_occurrence_only(const void* feat, const pasn_weights& w, const void* p
   return PASN_OK;
 }
 
+
+// =================================================================================================================
+// Backward of the head on the tensor cores (reference: loss.backward() through
+// Video_XProtoNet.forward, src/agents/XProtoNet_Base.py:397, src/models/Video_XProtoNet.py:82-98).
+//
+// Every contraction of the fp32 gradient (backward.cu documents the math and the sub-gradient conventions) runs as a
+// three-pass bf16 hi/lo GEMM of tc_gemm.cu over token-major planes, i.e. fp32-grade products with fp32 accumulation:
+//   recomputed forward   XT -> [H1|G1] -> G2 -> Opre (sign carrier + |.| planes) ; F = W2 H1 + b2 ; FE = O^T F
+//   prototype stage      gFE, gV, gWl                                     (two small CUDA-core kernels)
+//   gOpre = ((F gFE^T) + gOcc) * sign(Opre)          per clip, the upstream map gradient is read transposed
+//   gF    = O gFE                                    per clip
+//   gH1   = (gF W2) masked by H1 > 0 ; gG2 = (gOpre W5) masked ; gG1 = (gG2 W4) masked      (ReLU masks in the epilogue)
+//   weight gradients     gW[m][n] = sum_tokens gY[t][m] X[t][n]: both operands token-major (MN-major), the token range
+//                        split over the machine, fp32 partials reduced by one small kernel; biases: column sums
+//   gX    = [gH1|gG1] [W1;W3]                        stored channel-major per clip (NCDHW) in fp32
+// =================================================================================================================
+namespace {
+
+struct BPlan {
+  int C, D, D2, P, Pp, K, S, xe;   // xe: planes of the token-major feature copy (1: bf16 input is exact, 2: fp32 input)
+  int nb;
+  size_t off_pk, off_xt, off_y, off_g2, off_os, off_oa, off_f, off_fe, off_gfe, off_rs, off_go, off_gf, off_gy, off_gg2,
+      off_part, part_bytes, total;
+};
+
+inline int split_parts(long long T, int tiles, int* kper) {
+  int parts = (148 + tiles - 1) / tiles;
+  if (parts < 1) parts = 1;
+  long long k = (T + parts - 1) / parts;
+  if (k < 256) k = 256;
+  k = (k + 63) / 64 * 64;
+  *kper = (int)k;
+  return (int)((T + k - 1) / k);
+}
+
+BPlan make_bplan(const pasn_dims& d) {
+  BPlan b{};
+  b.C = d.C; b.D = d.D; b.D2 = d.D / 2; b.P = d.P; b.Pp = (d.P + 7) / 8 * 8; b.K = d.K; b.S = d.S;
+  b.xe = d.dtype == PASN_F32 ? 2 : 1;
+  pasn_dims d2 = d;
+  d2.dtype = PASN_F32;
+  const size_t pk = align_up(pack_layout(d2).total, 1024);
+  const size_t S = d.S;
+  const size_t per_tok = (size_t)b.xe * d.C * 2 + 4 * d.D * 2 + 2 * b.D2 * 2 + 3 * b.Pp * 2 + 2 * d.D * 2 +   // XT Y G2 OS OA F
+                         2 * b.Pp * 2 + 2 * d.D * 2 + 4 * d.D * 2 + 2 * b.D2 * 2;                             // GO GF GY GG2
+  const size_t per_clip = per_tok * S + (size_t)d.P * d.D * 4 + (size_t)d.P * 2 * d.D * 2 + (size_t)d.P * 16 + 4096;
+  // fp32 partials of the largest weight gradient at full machine width
+  const size_t m13 = (size_t)2 * d.D * d.C, m2 = (size_t)d.D * d.D;
+  b.part_bytes = align_up((m13 > m2 ? m13 : m2) * 4 * 80, 1024);
+  long long nb = (long long)(((size_t)1500 << 20) / per_clip);
+  if (nb < 1) nb = 1;
+  if (nb > d.N) nb = d.N > 0 ? d.N : 1;
+  b.nb = (int)nb;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  const size_t T = (size_t)b.nb * S;
+  b.off_pk = take(pk);
+  b.off_xt = take(T * b.xe * d.C * 2);
+  b.off_y = take(T * 4 * d.D * 2);
+  b.off_g2 = take(T * 2 * b.D2 * 2);
+  b.off_os = take(T * b.Pp * 2);
+  b.off_oa = take(T * 2 * b.Pp * 2);
+  b.off_f = take(T * 2 * d.D * 2);
+  b.off_fe = take((size_t)b.nb * d.P * d.D * 4);
+  b.off_gfe = take((size_t)b.nb * d.P * 2 * d.D * 2);
+  b.off_rs = take((size_t)b.nb * d.P * 16);
+  b.off_go = take(T * 2 * b.Pp * 2);
+  b.off_gf = take(T * 2 * d.D * 2);
+  b.off_gy = take(T * 4 * d.D * 2);
+  b.off_gg2 = take(T * 2 * b.D2 * 2);
+  b.off_part = take(b.part_bytes);
+  b.total = o + 256;
+  return b;
+}
+
+// three-pass product of two plane pairs; an operand without a lo plane (bf16-exact feature map) drops its pass
+void set_passes_b(tcg::Gemm& g, int a_lo, int b_lo, bool a_has_lo = true, bool b_has_lo = true) {
+  g.pair = 1;
+  for (int q = 0; q < 4; ++q) g.a_off[q] = g.b_off[q] = 0;
+  int n = 1;
+  if (b_has_lo) { g.b_off[n] = b_lo; ++n; }
+  if (a_has_lo) { g.a_off[n] = a_lo; ++n; }
+  g.npass = n;
+}
+
+// prototype stage backward, part 1: one warp per (clip, prototype) row.
+//   gs = gSim + sum_k gLogits[n,k] Wl[k,p];  gcos = gs / 2;  cos = <f,v> / (nf nv) with each norm clamped at eps (a clamped
+//   norm is a constant);  gFE = gcos (v / (nf nv) - cos f / nf^2)  -> bf16 hi|lo planes (operand of the next GEMMs);
+//   row scalars for part 2: a = gcos / (nf nv), b = gcos cos / nv^2 (0 when nv is clamped), sim
+__global__ void __launch_bounds__(256) proto_bwd_rows_kernel(const float* __restrict__ FE, const float* __restrict__ protos,
+                                                             const float* __restrict__ last_layer, const float* __restrict__ gLogits,
+                                                             const float* __restrict__ gSim, long long rows, int P, int D, int K,
+                                                             __nv_bfloat16* __restrict__ gfe, float4* __restrict__ rs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr float eps = 1e-8f;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    const long long n = r / P;
+    const int p = (int)(r - n * P);
+    const float* f = FE + (size_t)r * D;
+    const float* v = protos + (size_t)p * D;
+    float ff = 0.f, vv = 0.f, dot = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float a = f[d], b = v[d];
+      ff = fmaf(a, a, ff); vv = fmaf(b, b, vv); dot = fmaf(a, b, dot);
+    }
+    ff = warp_sum(ff); vv = warp_sum(vv); dot = warp_sum(dot);
+    const float fnorm = sqrtf(ff), vnorm = sqrtf(vv);
+    const float nf = fmaxf(fnorm, eps), nv = fmaxf(vnorm, eps);
+    const float inv = 1.0f / (nf * nv);
+    const float cosv = dot * inv;
+    float gs = gSim ? gSim[r] : 0.f;
+    if (gLogits)
+      for (int k = 0; k < K; ++k) gs = fmaf(gLogits[(size_t)n * K + k], last_layer[(size_t)k * P + p], gs);
+    const float gcos = 0.5f * gs;
+    const float cf = (fnorm > eps) ? cosv / (nf * nf) : 0.f;
+    const float cv = (vnorm > eps) ? cosv / (nv * nv) : 0.f;
+    __nv_bfloat16* grow = gfe + (size_t)r * 2 * D;
+    for (int d = lane; d < D; d += 32) {
+      const float gv = gcos * (v[d] * inv - cf * f[d]);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
+      grow[d] = hi;
+      grow[D + d] = __float2bfloat16_rn(gv - __bfloat162float(hi));
+    }
+    if (lane == 0) rs[r] = make_float4(gcos * inv, gcos * cv, (cosv + 1.0f) * 0.5f, 0.f);
+  }
+}
+// part 2: gV[p,:] += sum_n a[n,p] FE[n,p,:] - (sum_n b[n,p]) v[p,:];  gWl[k,p] += sum_n gLogits[n,k] sim[n,p].  Block per prototype.
+__global__ void __launch_bounds__(256) proto_bwd_reduce_kernel(const float* __restrict__ FE, const float* __restrict__ protos,
+                                                               const float* __restrict__ gLogits, const float4* __restrict__ rs,
+                                                               int nb, int P, int D, int K, float* __restrict__ gV,
+                                                               float* __restrict__ gWl) {
+  const int p = blockIdx.x, tid = threadIdx.x;
+  __shared__ float sb;
+  if (tid == 0) {
+    float b = 0.f;
+    for (int n = 0; n < nb; ++n) b += rs[(size_t)n * P + p].y;
+    sb = b;
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += 256) {
+    float acc = 0.f;
+    for (int n = 0; n < nb; ++n) acc = fmaf(rs[(size_t)n * P + p].x, FE[((size_t)n * P + p) * D + d], acc);
+    gV[(size_t)p * D + d] += acc - sb * protos[(size_t)p * D + d];
+  }
+  if (gLogits && tid < K) {
+    float acc = 0.f;
+    for (int n = 0; n < nb; ++n) acc = fmaf(gLogits[(size_t)n * K + tid], rs[(size_t)n * P + p].z, acc);
+    gWl[(size_t)tid * P + p] += acc;
+  }
+}
+
+// dst[m][n] += sum_parts part[q][m][n]; rows >= rows0 continue in dst1 (stacked [W1; W3] gradient)
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int M, int N, float* __restrict__ dst0, int rows0,
+                                    float* __restrict__ dst1) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  float a = 0.f;
+  for (int q = 0; q < nparts; ++q) a += part[(size_t)q * M * N + i];
+  const int m = (int)(i / N);
+  if (m < rows0) dst0[i] += a;
+  else dst1[i - (long long)rows0 * N] += a;
+}
+
+// gb[c] += sum over rows of (hi + lo) planes: X [rows][ld] with the lo plane at column lo_off; blocks of 32 columns x 256 rows
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ X, long long rows, long long ld,
+                                                            int lo_off, int ncols, float* __restrict__ gb0, int cols0,
+                                                            float* __restrict__ gb1) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const long long r0 = (long long)blockIdx.y * 2048;
+  float a = 0.f;
+  if (c < ncols) {
+    const long long r1 = r0 + 2048 < rows ? r0 + 2048 : rows;
+    for (long long r = r0 + wy; r < r1; r += 8) {
+      const __nv_bfloat16* row = X + r * ld;
+      a += __bfloat162float(row[c]) + __bfloat162float(row[lo_off + c]);
+    }
+  }
+  red[wy][lane] = a;
+  __syncthreads();
+  if (wy == 0 && c < ncols) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    atomicAdd(c < cols0 ? gb0 + c : gb1 + (c - cols0), t);
+  }
+}
+
+}  // namespace
+
+bool tiled_backward_supported(const pasn_dims& d) { return tiled_supported(d) && d.path != PASN_PATH_GENERIC; }
+size_t tiled_backward_workspace_bytes(const pasn_dims& d) { return make_bplan(d).total; }
+
+int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims& d, const float* gLogits, const float* gSim,
+                        const float* gOcc, const pasn_grads& gr, float* gX, void* ws_, size_t ws_bytes, cudaStream_t st) {
+  const BPlan b = make_bplan(d);
+  if (ws_bytes < b.total) return PASN_ERR_WORKSPACE;
+  if (((uintptr_t)ws_ & 255) != 0) return PASN_ERR_ALIGN;
+  char* ws = reinterpret_cast<char*>(ws_);
+  const int C = b.C, D = b.D, D2 = b.D2, P = b.P, Pp = b.Pp, S = b.S, xe = b.xe;
+  int rc;
+  // weight planes (hi | lo), the forward's fp32-mode packing
+  pasn_dims d2 = d;
+  d2.dtype = PASN_F32;
+  const PackLayout L = pack_layout(d2);
+  if ((rc = tiled_pack_weights(w, d2, ws + b.off_pk, st))) return rc;
+  const char* pk = ws + b.off_pk;
+  const __nv_bfloat16* W13 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w13);   // [2D][2C]
+  const __nv_bfloat16* W4 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w4);     // [D2][2D]
+  const __nv_bfloat16* W5 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w5);     // [P][2 D2]
+  const __nv_bfloat16* W2 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w2);     // [D][2D]
+  const float* b13 = reinterpret_cast<const float*>(pk + L.off_b13);
+  const float* b4 = reinterpret_cast<const float*>(pk + L.off_b4);
+  const float* b2 = reinterpret_cast<const float*>(pk + L.off_b2);
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  __nv_bfloat16 *XT = bf(b.off_xt), *Y = bf(b.off_y), *G2 = bf(b.off_g2), *OS = bf(b.off_os), *OA = bf(b.off_oa), *F = bf(b.off_f),
+                *GFE = bf(b.off_gfe), *GO = bf(b.off_go), *GF = bf(b.off_gf), *GY = bf(b.off_gy), *GG2 = bf(b.off_gg2);
+  float* FE = reinterpret_cast<float*>(ws + b.off_fe);
+  float4* RS = reinterpret_cast<float4*>(ws + b.off_rs);
+  float* PART = reinterpret_cast<float*>(ws + b.off_part);
+  const size_t elt = d.dtype == PASN_BF16 ? 2 : 4;
+  const bool x_lo = xe == 2;
+
+  // gW[m][n] (+)= sum_t A[t][m] B[t][n] over the tokens of the chunk (hi|lo planes, lo at column a_lo / b_lo)
+  auto wgrad = [&](const __nv_bfloat16* A, long long lda, int a_lo, int M, const __nv_bfloat16* B, long long ldb, int b_lo,
+                   bool b_has_lo, int N, long long T, float* dst0, int rows0, float* dst1) -> int {
+    const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+    const int tiles = ceil_div(M, 256) * ceil_div(N, bn) * 2;
+    int kper;
+    int parts = split_parts(T, tiles > 148 ? 148 : tiles, &kper);
+    while ((size_t)parts * M * N * 4 > b.part_bytes && parts > 1) { kper *= 2; parts = (int)((T + kper - 1) / kper); }
+    tcg::Gemm g{};
+    g.A = A; g.lda = lda; g.ka = (int)lda; g.a_mn_major = 1; g.a_rows = (int)T;
+    g.B = B; g.ldb = ldb; g.kb = (int)ldb; g.b_mn_major = 1; g.b_rows = (int)T;
+    g.M = M; g.N = N; g.K = kper; g.batch = parts; g.k_rows_per_batch = kper; g.bn = bn;
+    set_passes_b(g, a_lo, b_lo, true, b_has_lo);
+    g.out[0] = {PART, tcg::OUT_F32, (long long)N, (long long)M * N, 0, 0, 0, 0};
+    int r = tcg::launch(g, st);
+    if (r) return r;
+    const long long tot = (long long)M * N;
+    reduce_parts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(PART, parts, M, N, dst0, rows0, dst1 ? dst1 : dst0);
+    if (cudaGetLastError() != cudaSuccess) return PASN_ERR_CUDA;
+    count_launch();
+    return PASN_OK;
+  };
+  auto colsum = [&](const __nv_bfloat16* X, long long T, long long ld, int lo_off, int ncols, float* g0, int cols0, float* g1) -> int {
+    dim3 grid(ceil_div(ncols, 32), (unsigned)((T + 2047) / 2048));
+    colsum_planes_kernel<<<grid, 256, 0, st>>>(X, T, ld, lo_off, ncols, g0, cols0, g1 ? g1 : g0);
+    if (cudaGetLastError() != cudaSuccess) return PASN_ERR_CUDA;
+    count_launch();
+    return PASN_OK;
+  };
+
+  for (int n0 = 0; n0 < d.N; n0 += b.nb) {
+    const int nb = d.N - n0 < b.nb ? d.N - n0 : b.nb;
+    const long long T = (long long)nb * S;
+    const char* x = reinterpret_cast<const char*>(feat) + (size_t)n0 * C * S * elt;
+    // ---- token-major feature planes
+    const __nv_bfloat16* xt = XT;
+    if (d.layout == PASN_LAYOUT_NSC && xe == 1) {
+      xt = reinterpret_cast<const __nv_bfloat16*>(x);
+      if (((uintptr_t)xt & 15) != 0) return PASN_ERR_ALIGN;
+    } else if (d.layout == PASN_LAYOUT_NSC) {
+      to_tokens_nsc_f32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, C, XT);
+      count_launch();
+    } else {
+      dim3 grid(ceil_div(S, 32), ceil_div(C, 64), nb);
+      if (xe == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, 1, XT);
+      else to_tokens_ncs_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), C, S, 2, XT);
+      count_launch();
+    }
+    PASN_LAUNCH_CHECK();
+    const long long ldx = (long long)xe * C;
+
+    // ================= forward, recomputed
+    {  // [H1 | G1] = relu(X [W1; W3]^T + b)
+      tcg::Gemm g{};
+      g.A = xt; g.lda = ldx; g.ka = (int)ldx;
+      g.B = W13; g.ldb = 2 * C; g.kb = 2 * C;
+      g.M = (int)T; g.N = 2 * D; g.K = C; g.batch = 1; g.bn = 256;
+      set_passes_b(g, C, C, x_lo, true);
+      g.bias = b13; g.act = tcg::ACT_RELU;
+      g.out[0] = {Y, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {  // G2 = relu(G1 W4^T + b4)
+      tcg::Gemm g{};
+      g.A = Y + D; g.lda = 4 * D; g.ka = 4 * D - D;
+      g.B = W4; g.ldb = 2 * D; g.kb = 2 * D;
+      g.M = (int)T; g.N = D2; g.K = D; g.batch = 1; g.bn = pick_bn(D2);
+      set_passes_b(g, 2 * D, D);
+      g.bias = b4; g.act = tcg::ACT_RELU;
+      g.out[0] = {G2, tcg::OUT_BF16_HILO, (long long)2 * D2, 0, D2, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {  // Opre = G2 W5^T over all tokens: signed bf16 copy (sign carrier) and |.| as hi|lo planes; pad columns come out as zeros
+      tcg::Gemm g{};
+      g.A = G2; g.lda = 2 * D2; g.ka = 2 * D2;
+      g.B = W5; g.ldb = 2 * D2; g.kb = 2 * D2;
+      g.M = (int)T; g.N = P; g.K = D2; g.batch = 1; g.bn = pick_bn(P);
+      set_passes_b(g, D2, D2);
+      g.act = tcg::ACT_NONE;
+      g.out[0] = {OS, tcg::OUT_BF16, (long long)Pp, 0, 0, Pp, 0, 0};
+      g.out[1] = {OA, tcg::OUT_BF16_HILO, (long long)2 * Pp, 0, Pp, Pp, 1, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {  // F = H1 W2^T + b2
+      tcg::Gemm g{};
+      g.A = Y; g.lda = 4 * D; g.ka = 4 * D;
+      g.B = W2; g.ldb = 2 * D; g.kb = 2 * D;
+      g.M = (int)T; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
+      set_passes_b(g, 2 * D, D);
+      g.bias = b2;
+      g.out[0] = {F, tcg::OUT_BF16_HILO, (long long)2 * D, 0, D, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {  // FE[n] = O[n]^T F[n]   (K = S; both operands token-major)
+      tcg::Gemm g{};
+      g.A = OA; g.lda = 2 * Pp; g.a_bs = (long long)S * 2 * Pp; g.a_batched = 1; g.ka = 2 * Pp; g.a_mn_major = 1; g.a_rows = S;
+      g.B = F; g.ldb = 2 * D; g.b_bs = (long long)S * 2 * D; g.b_batched = 1; g.kb = 2 * D; g.b_mn_major = 1; g.b_rows = S;
+      g.M = P; g.N = D; g.K = S; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
+      set_passes_b(g, Pp, D);
+      g.out[0] = {FE, tcg::OUT_F32, (long long)D, (long long)P * D, 0, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    // ================= prototype stage
+    {
+      const long long rows = (long long)nb * P;
+      long long blocks = (rows + 7) / 8;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      proto_bwd_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(FE, w.prototypes, w.last_layer, gLogits ? gLogits + (size_t)n0 * d.K : nullptr,
+                                                              gSim ? gSim + (size_t)n0 * P : nullptr, rows, P, D, d.K, GFE, RS);
+      PASN_LAUNCH_CHECK();
+      count_launch();
+      proto_bwd_reduce_kernel<<<P, 256, 0, st>>>(FE, w.prototypes, gLogits ? gLogits + (size_t)n0 * d.K : nullptr, RS, nb, P, D, d.K,
+                                                 gr.prototypes, gr.last_layer);
+      PASN_LAUNCH_CHECK();
+      count_launch();
+    }
+    // ================= pooling backward
+    {  // gOpre[n][s][p] = ((F[n] gFE[n]^T)[s][p] + gOcc[n][p][s]) * sign(Opre[n][s][p])
+      tcg::Gemm g{};
+      g.A = F; g.lda = 2 * D; g.a_bs = (long long)S * 2 * D; g.a_batched = 1; g.ka = 2 * D;
+      g.B = GFE; g.ldb = 2 * D; g.b_bs = (long long)P * 2 * D; g.b_batched = 1; g.kb = 2 * D;
+      g.M = S; g.N = P; g.K = D; g.batch = nb; g.bn = pick_bn(P);
+      set_passes_b(g, D, D);
+      if (gOcc) g.addin = {gOcc + (size_t)n0 * P * S, 1, (long long)P * S, (long long)S};
+      g.signin = {OS, (long long)Pp, (long long)S * Pp, 0};
+      g.out[0] = {GO, tcg::OUT_BF16_HILO, (long long)2 * Pp, (long long)S * 2 * Pp, Pp, Pp, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    {  // gF[n][s][d] = sum_p O[n][s][p] gFE[n][p][d]
+      tcg::Gemm g{};
+      g.A = OA; g.lda = 2 * Pp; g.a_bs = (long long)S * 2 * Pp; g.a_batched = 1; g.ka = 2 * Pp;
+      g.B = GFE; g.ldb = 2 * D; g.b_bs = (long long)P * 2 * D; g.b_batched = 1; g.kb = 2 * D; g.b_mn_major = 1; g.b_rows = P;
+      g.M = S; g.N = D; g.K = P; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
+      set_passes_b(g, Pp, D);
+      g.out[0] = {GF, tcg::OUT_BF16_HILO, (long long)2 * D, (long long)S * 2 * D, D, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    // ================= add-on branch
+    if ((rc = wgrad(GF, 2 * D, D, D, Y, 4 * D, 2 * D, true, D, T, gr.addon_w2, D, nullptr))) return rc;     // gW2 += gF^T H1
+    if ((rc = colsum(GF, T, 2 * D, D, D, gr.addon_b2, D, nullptr))) return rc;
+    {  // gH1 = (gF W2) masked by H1 > 0   -> columns [0, D) of the [gH1 | gG1] planes
+      tcg::Gemm g{};
+      g.A = GF; g.lda = 2 * D; g.ka = 2 * D;
+      g.B = W2; g.ldb = 2 * D; g.kb = 2 * D; g.b_mn_major = 1; g.b_rows = D;
+      g.M = (int)T; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
+      set_passes_b(g, D, D);
+      g.mask = {Y, (long long)4 * D, 0, 0};
+      g.out[0] = {GY, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    // ================= occurrence branch
+    if ((rc = wgrad(GO, 2 * Pp, Pp, P, G2, 2 * D2, D2, true, D2, T, gr.occ_w3, P, nullptr))) return rc;      // gW5 += gOpre^T G2
+    {  // gG2 = (gOpre W5) masked by G2 > 0
+      tcg::Gemm g{};
+      g.A = GO; g.lda = 2 * Pp; g.ka = 2 * Pp;
+      g.B = W5; g.ldb = 2 * D2; g.kb = 2 * D2; g.b_mn_major = 1; g.b_rows = P;
+      g.M = (int)T; g.N = D2; g.K = P; g.batch = 1; g.bn = pick_bn(D2);
+      set_passes_b(g, Pp, D2);
+      g.mask = {G2, (long long)2 * D2, 0, 0};
+      g.out[0] = {GG2, tcg::OUT_BF16_HILO, (long long)2 * D2, 0, D2, 0, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    if ((rc = wgrad(GG2, 2 * D2, D2, D2, Y + D, 4 * D, 2 * D, true, D, T, gr.occ_w2, D2, nullptr))) return rc;   // gW4 += gG2^T G1
+    if ((rc = colsum(GG2, T, 2 * D2, D2, D2, gr.occ_b2, D2, nullptr))) return rc;
+    {  // gG1 = (gG2 W4) masked by G1 > 0   -> columns [D, 2D) of the [gH1 | gG1] planes
+      tcg::Gemm g{};
+      g.A = GG2; g.lda = 2 * D2; g.ka = 2 * D2;
+      g.B = W4; g.ldb = 2 * D; g.kb = 2 * D; g.b_mn_major = 1; g.b_rows = D2;
+      g.M = (int)T; g.N = D; g.K = D2; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
+      set_passes_b(g, D2, D);
+      g.mask = {Y + D, (long long)4 * D, 0, 0};
+      g.out[0] = {GY + D, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, D, 0, 0};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+    // ================= first layer: g[W1; W3] += [gH1 | gG1]^T X, biases, feature-map gradient
+    if ((rc = wgrad(GY, 4 * D, 2 * D, 2 * D, xt, ldx, C, x_lo, C, T, gr.addon_w1, D, gr.occ_w1))) return rc;
+    if ((rc = colsum(GY, T, 4 * D, 2 * D, 2 * D, gr.addon_b1, D, gr.occ_b1))) return rc;
+    if (gX) {   // gX[n][c][s] = sum_o [gH1|gG1][n,s][o] [W1;W3][o][c]
+      tcg::Gemm g{};
+      g.A = GY; g.lda = 4 * D; g.ka = 4 * D;
+      g.B = W13; g.ldb = 2 * C; g.kb = 2 * C; g.b_mn_major = 1; g.b_rows = 2 * D;
+      g.M = (int)T; g.N = C; g.K = 2 * D; g.batch = 1; g.bn = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+      set_passes_b(g, 2 * D, C);
+      g.out[0] = {gX + (size_t)n0 * C * S, tcg::OUT_F32, (long long)S, (long long)C * S, 0, 0, 0, S};
+      if ((rc = tcg::launch(g, st))) return rc;
+    }
+  }
+  return PASN_OK;
+}
+
 }  // namespace pasn

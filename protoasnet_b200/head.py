@@ -179,8 +179,8 @@ class _HeadFunction(torch.autograd.Function):
         rt = ctx.rt
         lib = _lib.load()
         m = rt.owner
-        dims, xc, spatial = rt.make_dims(x, _lib.PASN_PATH_GENERIC)
-        dev = xc.device
+        dims, xc, spatial = rt.make_dims(x, m.kernel_path)   # GENERIC keeps the CUDA-core backward, anything else lets the
+        dev = xc.device                                       # library pick the tensor-core chain when the shape qualifies
         with torch.cuda.device(dev), torch.no_grad():
             stream = torch.cuda.current_stream(dev).cuda_stream
             w, tensors = rt._weights_struct(m)
