@@ -388,15 +388,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const __nv_bfloat16* sg = g.signin.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.signin.ptr) + (long long)b * g.signin.bs + (long long)row * g.signin.ld : nullptr;
             const __nv_bfloat16* mk = g.mask.ptr ? reinterpret_cast<const __nv_bfloat16*>(g.mask.ptr) + (long long)b * g.mask.bs + (long long)row * g.mask.ld : nullptr;
             const long long acs = g.addin.cs ? g.addin.cs : 1, scs = g.signin.cs ? g.signin.cs : 1, mcs = g.mask.cs ? g.mask.cs : 1;
+            if (ad) {   // fp32, read along the rows (coalesced over the lanes when the array is transposed: ld = 1)
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const int col = col0 + j;
-              if (col < g.N) {
-                if (ad) v[j] += __ldg(ad + col * acs);
-                if (sg) { const float x = __bfloat162float(sg[col * scs]); v[j] = x > 0.f ? v[j] : (x < 0.f ? -v[j] : 0.f); }
-                if (mk) v[j] = __bfloat162float(mk[col * mcs]) > 0.f ? v[j] : 0.f;
-              }
+              for (int j = 0; j < 64; ++j)
+                if (col0 + j < g.N) v[j] += __ldg(ad + (col0 + j) * acs);
             }
+            // bf16 inputs with the tile's own orientation: this thread's 64 columns are 128 contiguous bytes, read as
+            // 16-byte vectors wherever a whole vector lies inside the row (scalar reads for a ragged tail / strided arrays)
+            auto apply_bf16 = [&](const __nv_bfloat16* src, long long cs, bool is_sign) {
+              const bool vec_ok = cs == 1 && ((reinterpret_cast<uintptr_t>(src + col0) & 15) == 0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c8 = col0 + 8 * q;
+                if (c8 >= g.N) break;
+                uint32_t wds[4];
+                if (vec_ok && c8 + 8 <= g.N) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c8));
+                  wds[0] = u.x; wds[1] = u.y; wds[2] = u.z; wds[3] = u.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int ca = c8 + 2 * e, cb = ca + 1;
+                    const uint32_t lo = ca < g.N ? (uint32_t)__bfloat16_as_ushort(src[ca * cs]) : 0u;
+                    const uint32_t hi = cb < g.N ? (uint32_t)__bfloat16_as_ushort(src[cb * cs]) : 0u;
+                    wds[e] = lo | (hi << 16);
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  // bf16 -> fp32 is a 16-bit shift; only sign and zero-ness matter here
+                  const float x = __uint_as_float((e & 1) ? (wds[e >> 1] & 0xFFFF0000u) : (wds[e >> 1] << 16));
+                  float& y = v[8 * q + e];
+                  if (is_sign) y = x > 0.f ? y : (x < 0.f ? -y : 0.f);
+                  else y = x > 0.f ? y : 0.f;
+                }
+              }
+            };
+            if (sg) apply_bf16(sg, scs, true);
+            if (mk) apply_bf16(mk, mcs, false);
           }
         }
         if (g.psum != nullptr) {

@@ -555,28 +555,34 @@ __global__ void __launch_bounds__(256) proto_bwd_rows_kernel(const float* __rest
     if (lane == 0) rs[r] = make_float4(gcos * inv, gcos * cv, (cosv + 1.0f) * 0.5f, 0.f);
   }
 }
-// part 2: gV[p,:] += sum_n a[n,p] FE[n,p,:] - (sum_n b[n,p]) v[p,:];  gWl[k,p] += sum_n gLogits[n,k] sim[n,p].  Block per prototype.
+// part 2: gV[p,:] += sum_n a[n,p] FE[n,p,:] - (sum_n b[n,p]) v[p,:];  gWl[k,p] += sum_n gLogits[n,k] sim[n,p].
+// grid (P, slices of the clip range); every slice adds its share with atomics
 __global__ void __launch_bounds__(256) proto_bwd_reduce_kernel(const float* __restrict__ FE, const float* __restrict__ protos,
                                                                const float* __restrict__ gLogits, const float4* __restrict__ rs,
                                                                int nb, int P, int D, int K, float* __restrict__ gV,
                                                                float* __restrict__ gWl) {
   const int p = blockIdx.x, tid = threadIdx.x;
-  __shared__ float sb;
-  if (tid == 0) {
-    float b = 0.f;
-    for (int n = 0; n < nb; ++n) b += rs[(size_t)n * P + p].y;
-    sb = b;
-  }
+  const int per = (nb + gridDim.y - 1) / gridDim.y;
+  const int n_begin = blockIdx.y * per, n_end = min(nb, n_begin + per);
+  if (n_begin >= n_end) return;
+  __shared__ float red[8];
+  float bsum = 0.f;
+  for (int n = n_begin + tid; n < n_end; n += 256) bsum += rs[(size_t)n * P + p].y;
+  bsum = warp_sum(bsum);
+  if ((tid & 31) == 0) red[tid >> 5] = bsum;
   __syncthreads();
+  float sb = 0.f;
+  for (int i = 0; i < 8; ++i) sb += red[i];
   for (int d = tid; d < D; d += 256) {
     float acc = 0.f;
-    for (int n = 0; n < nb; ++n) acc = fmaf(rs[(size_t)n * P + p].x, FE[((size_t)n * P + p) * D + d], acc);
-    gV[(size_t)p * D + d] += acc - sb * protos[(size_t)p * D + d];
+#pragma unroll 4
+    for (int n = n_begin; n < n_end; ++n) acc = fmaf(rs[(size_t)n * P + p].x, FE[((size_t)n * P + p) * D + d], acc);
+    atomicAdd(gV + (size_t)p * D + d, acc - sb * protos[(size_t)p * D + d]);
   }
   if (gLogits && tid < K) {
     float acc = 0.f;
-    for (int n = 0; n < nb; ++n) acc = fmaf(gLogits[(size_t)n * K + tid], rs[(size_t)n * P + p].z, acc);
-    gWl[(size_t)tid * P + p] += acc;
+    for (int n = n_begin; n < n_end; ++n) acc = fmaf(gLogits[(size_t)n * K + tid], rs[(size_t)n * P + p].z, acc);
+    atomicAdd(gWl + (size_t)tid * P + p, acc);
   }
 }
 
@@ -592,28 +598,34 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, 
   else dst1[i - (long long)rows0 * N] += a;
 }
 
-// gb[c] += sum over rows of (hi + lo) planes: X [rows][ld] with the lo plane at column lo_off; blocks of 32 columns x 256 rows
+// gb[c] += sum over rows of (hi + lo) planes: X [rows][ld] with the lo plane at column lo_off.  A warp covers 64 columns
+// (one bf16 pair per lane and plane: 128-byte row segments), a block 8 x 32 rows per step; grid (ncols / 64, row chunks)
 __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ X, long long rows, long long ld,
                                                             int lo_off, int ncols, float* __restrict__ gb0, int cols0,
                                                             float* __restrict__ gb1) {
-  __shared__ float red[8][33];
+  __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const long long r0 = (long long)blockIdx.y * 2048;
-  float a = 0.f;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const long long r0 = (long long)blockIdx.y * 512, r1 = r0 + 512 < rows ? r0 + 512 : rows;
+  float a0 = 0.f, a1 = 0.f;
   if (c < ncols) {
-    const long long r1 = r0 + 2048 < rows ? r0 + 2048 : rows;
+#pragma unroll 4
     for (long long r = r0 + wy; r < r1; r += 8) {
       const __nv_bfloat16* row = X + r * ld;
-      a += __bfloat162float(row[c]) + __bfloat162float(row[lo_off + c]);
+      const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
+      const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + lo_off + c));
+      a0 += h.x + l.x; a1 += h.y + l.y;
     }
   }
-  red[wy][lane] = a;
+  red[wy][2 * lane] = a0; red[wy][2 * lane + 1] = a1;
   __syncthreads();
-  if (wy == 0 && c < ncols) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i][lane];
-    atomicAdd(c < cols0 ? gb0 + c : gb1 + (c - cols0), t);
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < ncols) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      atomicAdd(cc < cols0 ? gb0 + cc : gb1 + (cc - cols0), t);
+    }
   }
 }
 
@@ -675,7 +687,7 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
     return PASN_OK;
   };
   auto colsum = [&](const __nv_bfloat16* X, long long T, long long ld, int lo_off, int ncols, float* g0, int cols0, float* g1) -> int {
-    dim3 grid(ceil_div(ncols, 32), (unsigned)((T + 2047) / 2048));
+    dim3 grid(ceil_div(ncols, 64), (unsigned)((T + 511) / 512));   // ncols is even on every caller (channel counts)
     colsum_planes_kernel<<<grid, 256, 0, st>>>(X, T, ld, lo_off, ncols, g0, cols0, g1 ? g1 : g0);
     if (cudaGetLastError() != cudaSuccess) return PASN_ERR_CUDA;
     count_launch();
@@ -763,7 +775,7 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
                                                               gSim ? gSim + (size_t)n0 * P : nullptr, rows, P, D, d.K, GFE, RS);
       PASN_LAUNCH_CHECK();
       count_launch();
-      proto_bwd_reduce_kernel<<<P, 256, 0, st>>>(FE, w.prototypes, gLogits ? gLogits + (size_t)n0 * d.K : nullptr, RS, nb, P, D, d.K,
+      proto_bwd_reduce_kernel<<<dim3(P, nb >= 64 ? 16 : 1), 256, 0, st>>>(FE, w.prototypes, gLogits ? gLogits + (size_t)n0 * d.K : nullptr, RS, nb, P, D, d.K,
                                                  gr.prototypes, gr.last_layer);
       PASN_LAUNCH_CHECK();
       count_launch();
