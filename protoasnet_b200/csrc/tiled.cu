@@ -629,6 +629,32 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
   }
 }
 
+// occurrence-only backward: gOpre[(n,s)][p] = gOcc[n][p][s] * sign(Opre[(n,s)][p]) as hi|lo planes (32 x 32 tiles through
+// shared memory: reads run along s, writes along p); pad columns [P, Pp) are written as zeros
+__global__ void __launch_bounds__(256) gopre_from_gocc_kernel(const float* __restrict__ gOcc, const __nv_bfloat16* __restrict__ OS,
+                                                              int P, int Pp, int S, __nv_bfloat16* __restrict__ GO) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, s = s0 + tx;
+    tile[j][tx] = (p < P && s < S) ? gOcc[((size_t)n * P + p) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int s = s0 + j, p = p0 + tx;
+    if (s < S && p < Pp) {
+      const size_t t = (size_t)n * S + s;
+      float v = tile[tx][j];
+      const float o = __bfloat162float(OS[t * Pp + p]);
+      v = o > 0.f ? v : (o < 0.f ? -v : 0.f);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      GO[t * 2 * Pp + p] = hi;
+      GO[t * 2 * Pp + Pp + p] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
 }  // namespace
 
 bool tiled_backward_supported(const pasn_dims& d) { return tiled_supported(d) && d.path != PASN_PATH_GENERIC; }
@@ -663,6 +689,13 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
   float* PART = reinterpret_cast<float*>(ws + b.off_part);
   const size_t elt = d.dtype == PASN_BF16 ? 2 : 4;
   const bool x_lo = xe == 2;
+  // No gradient arrives through logits / similarity: backward of compute_occurence_map alone (TransformLoss re-entry,
+  // src/loss/loss.py:302) -- only the occurrence branch is recomputed and differentiated.
+  const bool occ_only = gLogits == nullptr && gSim == nullptr;
+  if (occ_only && gOcc == nullptr) {
+    if (gX) cudaMemsetAsync(gX, 0, (size_t)d.N * C * S * 4, st);
+    return PASN_OK;
+  }
 
   // gW[m][n] (+)= sum_t A[t][m] B[t][n] over the tokens of the chunk (hi|lo planes, lo at column a_lo / b_lo)
   auto wgrad = [&](const __nv_bfloat16* A, long long lda, int a_lo, int M, const __nv_bfloat16* B, long long ldb, int b_lo,
@@ -724,6 +757,10 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
       set_passes_b(g, C, C, x_lo, true);
       g.bias = b13; g.act = tcg::ACT_RELU;
       g.out[0] = {Y, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, 0, 0, 0};
+      if (occ_only) {   // G1 alone, into its usual columns [D, 2D) of the planes
+        g.B = W13 + (size_t)D * 2 * C; g.N = D; g.bias = b13 + D; g.bn = D >= 256 ? 256 : 128;
+        g.out[0] = {Y + D, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, D, 0, 0};
+      }
       if ((rc = tcg::launch(g, st))) return rc;
     }
     {  // G2 = relu(G1 W4^T + b4)
@@ -744,9 +781,15 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
       set_passes_b(g, D2, D2);
       g.act = tcg::ACT_NONE;
       g.out[0] = {OS, tcg::OUT_BF16, (long long)Pp, 0, 0, Pp, 0, 0};
-      g.out[1] = {OA, tcg::OUT_BF16_HILO, (long long)2 * Pp, 0, Pp, Pp, 1, 0};
+      if (!occ_only) g.out[1] = {OA, tcg::OUT_BF16_HILO, (long long)2 * Pp, 0, Pp, Pp, 1, 0};
       if ((rc = tcg::launch(g, st))) return rc;
     }
+    if (occ_only) {
+      dim3 grid(ceil_div(S, 32), ceil_div(Pp, 32), nb);
+      gopre_from_gocc_kernel<<<grid, 256, 0, st>>>(gOcc + (size_t)n0 * P * S, OS, P, Pp, S, GO);
+      PASN_LAUNCH_CHECK();
+      count_launch();
+    } else {
     {  // F = H1 W2^T + b2
       tcg::Gemm g{};
       g.A = Y; g.lda = 4 * D; g.ka = 4 * D;
@@ -814,6 +857,7 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
       g.out[0] = {GY, tcg::OUT_BF16_HILO, (long long)4 * D, 0, 2 * D, 0, 0, 0};
       if ((rc = tcg::launch(g, st))) return rc;
     }
+    }   // !occ_only
     // ================= occurrence branch
     if ((rc = wgrad(GO, 2 * Pp, Pp, P, G2, 2 * D2, D2, true, D2, T, gr.occ_w3, P, nullptr))) return rc;      // gW5 += gOpre^T G2
     {  // gG2 = (gOpre W5) masked by G2 > 0
@@ -839,14 +883,22 @@ int tiled_head_backward(const void* feat, const pasn_weights& w, const pasn_dims
       if ((rc = tcg::launch(g, st))) return rc;
     }
     // ================= first layer: g[W1; W3] += [gH1 | gG1]^T X, biases, feature-map gradient
-    if ((rc = wgrad(GY, 4 * D, 2 * D, 2 * D, xt, ldx, C, x_lo, C, T, gr.addon_w1, D, gr.occ_w1))) return rc;
-    if ((rc = colsum(GY, T, 4 * D, 2 * D, 2 * D, gr.addon_b1, D, gr.occ_b1))) return rc;
+    if (occ_only) {
+      if ((rc = wgrad(GY + D, 4 * D, 2 * D, D, xt, ldx, C, x_lo, C, T, gr.occ_w1, D, nullptr))) return rc;
+      if ((rc = colsum(GY + D, T, 4 * D, 2 * D, D, gr.occ_b1, D, nullptr))) return rc;
+    } else {
+      if ((rc = wgrad(GY, 4 * D, 2 * D, 2 * D, xt, ldx, C, x_lo, C, T, gr.addon_w1, D, gr.occ_w1))) return rc;
+      if ((rc = colsum(GY, T, 4 * D, 2 * D, 2 * D, gr.addon_b1, D, gr.occ_b1))) return rc;
+    }
     if (gX) {   // gX[n][c][s] = sum_o [gH1|gG1][n,s][o] [W1;W3][o][c]
       tcg::Gemm g{};
       g.A = GY; g.lda = 4 * D; g.ka = 4 * D;
       g.B = W13; g.ldb = 2 * C; g.kb = 2 * C; g.b_mn_major = 1; g.b_rows = 2 * D;
       g.M = (int)T; g.N = C; g.K = 2 * D; g.batch = 1; g.bn = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
       set_passes_b(g, 2 * D, C);
+      if (occ_only) {   // the G1 half alone: gG1 [W3]
+        g.A = GY + D; g.ka = 4 * D - D; g.B = W13 + (size_t)D * 2 * C; g.b_rows = D; g.K = D;
+      }
       g.out[0] = {gX + (size_t)n0 * C * S, tcg::OUT_F32, (long long)S, (long long)C * S, 0, 0, 0, S};
       if ((rc = tcg::launch(g, st))) return rc;
     }

@@ -161,6 +161,65 @@ class _HeadRuntime:
         return occ
 
 
+def _library_backward(ctx_rt, x, g_logits, g_sim, g_occ, want_gx):
+    """pasn_head_backward on (x, head parameters): returns (grad_x or None, [11 parameter gradients]).  With g_logits and
+    g_sim both None only the occurrence branch is differentiated (compute_occurence_map)."""
+    rt = ctx_rt
+    lib = _lib.load()
+    m = rt.owner
+    dims, xc, spatial = rt.make_dims(x, m.kernel_path)   # GENERIC keeps the CUDA-core backward, anything else lets the
+    dev = xc.device                                       # library pick the tensor-core chain when the shape qualifies
+    with torch.cuda.device(dev), torch.no_grad():
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        w, tensors = rt._weights_struct(m)
+        grads = [torch.zeros_like(t) for t in tensors]
+        gw = PasnGrads(*[g.data_ptr() for g in grads])
+        gx = torch.empty((dims.N, dims.C, dims.S), dtype=torch.float32, device=dev) if want_gx else None
+
+        def prep(g, shape):
+            if g is None:
+                return None
+            return g.to(torch.float32).reshape(shape).contiguous()
+
+        gl = prep(g_logits, (dims.N, dims.K))
+        gs = prep(g_sim, (dims.N, dims.P))
+        go = prep(g_occ, (dims.N, dims.P, dims.S))
+        if dims.N > 0:
+            need = int(lib.pasn_head_backward_workspace_bytes(C.byref(dims)))
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+            st = lib.pasn_head_backward(xc.data_ptr(), C.byref(w), C.byref(dims), _ptr(gl), _ptr(gs), _ptr(go),
+                                        C.byref(gw), _ptr(gx), ws.data_ptr(), ws.numel(), stream)
+            _lib.check(st, "pasn_head_backward")
+        elif gx is not None:
+            gx.zero_()
+    if gx is not None:
+        gx = gx.reshape((dims.N, dims.C) + spatial).to(x.dtype)
+    return gx, grads
+
+
+class _OccFunction(torch.autograd.Function):
+    """(features, occurrence_module parameters) -> occurrence_map with gradients: compute_occurence_map under grad, which
+    the reference's TransformLoss calls once more per training step (src/loss/loss.py:302).  Forward = the library's
+    occurrence-only path, backward = pasn_head_backward with no logits / similarity gradient (occurrence branch only)."""
+
+    @staticmethod
+    def forward(ctx, rt, x, *params):
+        with torch.no_grad():
+            occ = rt.occurrence_only(x)
+        ctx.rt = rt
+        ctx.save_for_backward(x, *params)
+        return occ
+
+    @staticmethod
+    def backward(ctx, g_occ):
+        x, *params = ctx.saved_tensors
+        gx, grads = _library_backward(ctx.rt, x, None, None, g_occ, ctx.needs_input_grad[1])
+        out = [None, gx]
+        for i in range(5):   # occ_w1, occ_b1, occ_w2, occ_b2, occ_w3 = entries 4..8 of the weight struct
+            out.append(grads[4 + i].reshape(params[i].shape) if ctx.needs_input_grad[2 + i] else None)
+        return tuple(out)
+
+
 class _HeadFunction(torch.autograd.Function):
     """(features, 11 head parameters) -> (logits, similarity, occurrence_map): forward through the library's usual path,
     backward through ``pasn_head_backward`` (fp32 CUDA-core kernels, forward intermediates recomputed)."""
@@ -176,37 +235,8 @@ class _HeadFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_logits, g_sim, g_occ):
         x, *params = ctx.saved_tensors
-        rt = ctx.rt
-        lib = _lib.load()
-        m = rt.owner
-        dims, xc, spatial = rt.make_dims(x, m.kernel_path)   # GENERIC keeps the CUDA-core backward, anything else lets the
-        dev = xc.device                                       # library pick the tensor-core chain when the shape qualifies
-        with torch.cuda.device(dev), torch.no_grad():
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            w, tensors = rt._weights_struct(m)
-            grads = [torch.zeros_like(t) for t in tensors]
-            gw = PasnGrads(*[g.data_ptr() for g in grads])
-            want_gx = ctx.needs_input_grad[1]
-            gx = torch.empty((dims.N, dims.C, dims.S), dtype=torch.float32, device=dev) if want_gx else None
-
-            def prep(g, shape):
-                if g is None:
-                    return None
-                return g.to(torch.float32).reshape(shape).contiguous()
-
-            gl = prep(g_logits, (dims.N, dims.K))
-            gs = prep(g_sim, (dims.N, dims.P))
-            go = prep(g_occ, (dims.N, dims.P, dims.S))
-            if dims.N > 0:
-                need = int(lib.pasn_head_backward_workspace_bytes(C.byref(dims)))
-                ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-                st = lib.pasn_head_backward(xc.data_ptr(), C.byref(w), C.byref(dims), _ptr(gl), _ptr(gs), _ptr(go),
-                                            C.byref(gw), _ptr(gx), ws.data_ptr(), ws.numel(), stream)
-                _lib.check(st, "pasn_head_backward")
-            elif gx is not None:
-                gx.zero_()
-        if gx is not None:
-            gx = gx.reshape((dims.N, dims.C) + spatial).to(x.dtype)
+        gx, grads = _library_backward(ctx.rt, x, g_logits, g_sim, g_occ, ctx.needs_input_grad[1])
+        tensors = grads
         out = [None, gx]
         for i, t in enumerate(tensors):
             out.append(grads[i].reshape(params[i].shape) if ctx.needs_input_grad[2 + i] else None)
@@ -425,6 +455,9 @@ class PrototypeHeadMixin:
         """-> occurrence_map [N,P,1,(T),H,W].  Video_XProtoNet.py:100-109."""
         x = self.cnn_backbone(x)
         if self._grad_guard(x):
+            if self.autograd_mode == "kernel":
+                o = self.occurrence_module
+                return _OccFunction.apply(self._rt, x, o[0].weight, o[0].bias, o[2].weight, o[2].bias, o[4].weight)
             return torch.abs(self.occurrence_module(x)).unsqueeze(2)
         return self._rt.occurrence_only(x)
 

@@ -118,3 +118,31 @@ def test_kernel_backward_cfg3_shape(dtype):
         assert_close(own[k].grad.reshape(ref_g[k].shape), ref_g[k], rtol, f"grad {k}", atol_frac=afrac)
     assert xt.grad.dtype == dtype
     assert_close(xt.grad, ref_gx, rtol, "grad feature map", atol_frac=afrac)
+
+
+@pytest.mark.parametrize("cfg,n,dtype", [("tiny_video", 5, torch.float32), ("cfg3_video_b1024", 4, torch.float32),
+                                         ("cfg3_video_b1024", 4, torch.bfloat16), ("cfg2_image", 6, torch.float32)])
+def test_compute_occurence_map_backward(cfg, n, dtype):
+    """compute_occurence_map under grad (TransformLoss re-entry, src/loss/loss.py:302) through the library: only the
+    occurrence branch is differentiated -- occurrence_module parameters and the feature map get gradients, nothing else."""
+    dims = synth.CONFIGS[cfg]
+    bf = dtype == torch.bfloat16
+    sd = synth.make_head_params(dims, seed=31, bias_scale=0.05, bf16_round=True)
+    x = synth.make_features(dims, n, seed=9, bf16_round=True)
+    wo = np.random.default_rng(4).standard_normal((n, dims.P, 1) + dims.spatial).astype(np.float32) * 0.1
+    _, ref_gx, ref_g = _oracle_grads(x, sd, np.zeros((n, dims.K), np.float32), np.zeros((n, dims.P), np.float32), wo)
+    m = build_model(dims, sd)
+    m.train()
+    m.autograd_mode = "kernel"
+    xt = torch.from_numpy(x).cuda().to(dtype).requires_grad_(True)
+    occ = m.compute_occurence_map(xt)
+    assert occ.shape == (n, dims.P, 1) + dims.spatial and occ.requires_grad
+    (occ.float() * torch.from_numpy(wo).cuda()).sum().backward()
+    own = dict(m.named_parameters())
+    rtol, afrac = (1e-2, 4e-3) if bf else (2e-4, 2e-5)
+    for k in KEYS:
+        if k.startswith("occurrence_module"):
+            assert_close(own[k].grad.reshape(ref_g[k].shape), ref_g[k], rtol, f"grad {k}", atol_frac=afrac)
+        else:
+            assert own[k].grad is None, k
+    assert_close(xt.grad, ref_gx, rtol, "grad feature map", atol_frac=afrac)
