@@ -520,7 +520,9 @@ int launch(const Gemm& g, cudaStream_t st) {
     attr_done = true;
   }
   static const int pair_env = [] { const char* e = getenv("PASN_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // A/B switch
-  const bool pair = (pair_env >= 0 ? pair_env != 0 : g.pair != 0) && g.bn >= 128 && g.M > BM;
+  // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py); short-K GEMMs are bound by
+  // their epilogues and lose a little to the cross-CTA hand-offs
+  const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= 8)) && g.bn >= 128 && g.M > BM;
   int* fault = fault_word();   // bounded waits report into the host-mapped sticky fault word
   if (fault == nullptr) return PASN_ERR_CUDA;
   KParams kp;
