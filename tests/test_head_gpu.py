@@ -8,7 +8,7 @@ import torch
 
 from oracle import head_oracle as ho
 from protoasnet_b200 import _lib, synth
-from tests.util import BF16_RTOL, FP32_RTOL, assert_close, build_model, feat_atol, load_golden
+from tests.util import FP32_TC_FEAT_ATOL, BF16_RTOL, FP32_RTOL, assert_close, build_model, feat_atol, load_golden
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -243,6 +243,50 @@ def test_tcgen05_path_shape_sweep(shape):
     assert_close(out["features_extracted"], ref["features_extracted"].cpu().numpy(), 4e-3, "features vs generic")
     assert_close(out["occurrence_map"], ref["occurrence_map"].float().cpu().numpy(), 2e-2, "occ vs generic", atol_frac=1e-2)
     assert torch.equal(out["distance"], 1 - out["similarity"])
+
+
+TILED_SHAPES = [
+    # C, D, P, K, spatial, n       (C a multiple of 64, D of 128: what the tiled GEMM chain takes)
+    (64, 128, 9, 3, (7,  7), 5),          # odd P and S: unaligned map rows -> plain stores; W2 before the pooling
+    (128, 128, 33, 3, (1, 5, 10), 3),     # P just over a 32-column group, S = 50 (16-byte aligned rows)
+    (64, 256, 130, 5, (3, 3, 3), 2),      # P over one 128-row tile, S = 27
+    (192, 128, 8, 2, (2, 10, 12), 7),     # S = 240 > 2P: W2 after the pooling (row sums, rank-1 bias term)
+    (512, 512, 40, 4, (7, 7), 11),        # the image head
+    (64, 128, 72, 4, (4, 16, 16), 2),     # P > 64: occurrence GEMM per clip, S = 1024 (aligned: no transposition in bf16)
+    (64, 128, 16, 4, (8,), 1),            # a single tiny clip (sequence-like [N,C,L] is not a valid map: goes through ndim check)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("layout", ["ncs", "nsc"])
+@pytest.mark.parametrize("shape", TILED_SHAPES[:-1], ids=[str(s) for s in TILED_SHAPES[:-1]])
+def test_tiled_path_shape_sweep(shape, layout, dtype):
+    """The tiled tensor-core chain (explicitly requested) on ragged shapes, both layouts and dtypes, against the CPU oracle."""
+    C, D, P, K, spatial, n = shape
+    dims = synth.HeadDims(C, D, P, K, spatial)
+    bf = dtype == torch.bfloat16
+    sd = synth.make_head_params(dims, seed=43, bias_scale=0.05, last_layer_noise=0.1, bf16_round=bf)
+    x = synth.make_features(dims, n, seed=29, bf16_round=bf)
+    m = build_model(dims, sd, path=_lib.PASN_PATH_TILED)        # errors out if the tiled path cannot take the shape
+    xg = torch.from_numpy(x).cuda().to(dtype)
+    if layout == "nsc":
+        xg = xg.contiguous(memory_format=torch.channels_last_3d if dims.ndim == 3 else torch.channels_last)
+    out = _run_all(m, xg)
+    with torch.no_grad():
+        rf, rd, ro, rl = ho.push_forward_torch(torch.from_numpy(x), ho.to_torch_sd(sd))
+    tol = BF16_RTOL if bf else FP32_RTOL
+    assert_close(out["similarity"], (1 - rd).numpy(), tol, "similarity")
+    assert_close(out["logits"], rl.numpy(), tol, "logits")
+    assert torch.equal(out["distance"], 1 - out["similarity"])
+    assert torch.equal(out["logits"], out["logits2"])
+    if bf:
+        assert_close(out["features_extracted"], rf.numpy(), 4e-3, "features_extracted", atol_frac=1e-3)
+        for k in ("occurrence_map", "occ2", "occ3"):
+            assert_close(out[k], ro.numpy(), 2e-2, k, atol_frac=1e-2)
+    else:
+        for k in ("occurrence_map", "occ2", "occ3"):
+            assert_close(out[k], ro.numpy(), FP32_RTOL, k, atol_frac=FP32_TC_FEAT_ATOL)
+        assert_close(out["features_extracted"], rf.numpy(), FP32_RTOL, "features_extracted", atol_frac=FP32_TC_FEAT_ATOL)
 
 
 def test_tcgen05_path_refuses_unsupported_shapes():
