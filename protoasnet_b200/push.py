@@ -178,7 +178,13 @@ def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_of
     ``labels`` int64 [n_local]); ``global_offset`` = global index of local clip 0.  This is the path bench.py times."""
     dev = features.device
     P, D = model.num_prototypes, model.prototype_shape[1]
-    pc = proto_class_restriction(model, class_specific, abstain_class).to(dev)
+    # the class restriction only depends on the (fixed) prototype_class_identity buffer: built once per model / device, so a
+    # push issues no host->device copy of its own (at 8 GPUs the fixed cost of a push is what limits its scaling)
+    ck = (bool(class_specific), bool(abstain_class), str(dev))
+    cache = model.__dict__.setdefault("_pasn_push_pc", {})
+    pc = cache.get(ck)
+    if pc is None:
+        pc = cache[ck] = proto_class_restriction(model, class_specific, abstain_class).to(dev)
     rec = PushRecord(P, D, dev)
     n_local = features.shape[0]
     for i in range(0, n_local, chunk):
