@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         for (int j = 0; j < g.nparts; ++j) rowterm += rp[j];
       }
       float psum = 0.f;
-      if (has_vec && h < nh) {   // bias / colvec slices of this warp's groups -> per-warp smem, before the accumulator is due
+      if (has_vec && h < nh && m0 + q * 32 < g.M) {   // bias / colvec slices of this warp's groups -> per-warp smem, before the accumulator is due
         __syncwarp();
         for (int cg = 0; cg < ngroups; ++cg) {
           const int colb = n0 + h * half_cols + 64 * cg;
@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       }
       if (!(ok = bwait(&bars[B_ACCFULL + buf], (i >> 1) & 1, kp.err, 721))) break;
       tc_fence_after();
-      if (h >= nh) {   // nothing to read for this warp: release the accumulator, keep the psum table dense
+      if (h >= nh || m0 + q * 32 >= g.M) {
+        // nothing to read for this warp (unused column half, or all 32 rows past M: the per-clip GEMMs with M = P = 40 only
+        // need two of the four row groups): release the accumulator, keep the psum table dense
         __syncwarp();
         if (lane == 0) acc_release(buf);
         if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = 0.f;
