@@ -103,12 +103,14 @@ def push_prototypes_oracle(
     from .head_oracle import push_forward_torch, to_torch_sd
     import torch
 
-    from protoasnet_b200.synth import prototype_class_identity as pci
-
     tsd = to_torch_sd(sd)
     pf = push_forward or push_forward_torch
     P = sd["prototype_vectors"].shape[0]
-    ident = pci(P, num_classes)
+    # one-hot class map of the reference (src/models/ProtoPNet.py:326-340): prototype j belongs to class j // (P / K);
+    # restated here so that the oracle does not lean on product code
+    assert P % num_classes == 0, "num_prototypes must be divisible by num_classes"
+    ident = np.zeros((P, num_classes), dtype=np.float32)
+    ident[np.arange(P), np.arange(P) // (P // num_classes)] = 1.0
 
     def gen():
         with torch.no_grad():
