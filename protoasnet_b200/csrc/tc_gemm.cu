@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue
-    const int w = warp - EPI_WARP0, q = w & 3, h = w >> 2;
+    const int w = warp - EPI_WARP0, q = w & 3, hw = w >> 2;
     const uint32_t tl = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t slab0 = sbase + SM_STG + (uint32_t)w * 2u * SLAB_BYTES;
     float* vecs_w = reinterpret_cast<float*>(smem + SM_VEC + w * 1024);   // per group: [0,64) bias slice, [64,128) colvec slice
@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const bool has_vec = g.bias != nullptr || (g.rowparts != nullptr && g.colvec != nullptr);
     const bool has_aux = g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr;
     const int nh = bn >= 128 ? 2 : 1;            // column halves in use (a 64-wide tile is one 64-column group: half 0 only)
+    // a 64-wide tile with two outputs: the second warp group, otherwise idle, reads the same columns and takes output 1
+    // (the channel-major plain stores of the occurrence map run next to the TMA store of the token-major copy)
+    const bool split_out = nh == 1 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE;
+    const int h = split_out ? 0 : hw;            // column half this warp reads
     const int half_cols = bn / nh;
     const int ngroups = half_cols / 64;
     uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         // need two of the four row groups): release the accumulator, keep the psum table dense
         __syncwarp();
         if (lane == 0) acc_release(buf);
-        if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = 0.f;
+        if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = 0.f;
         continue;
       }
       for (int cg = 0; cg < ngroups; ++cg) {
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           const Output& o = g.out[mi];
-          if (o.mode == OUT_NONE) continue;
+          if (o.mode == OUT_NONE || (split_out && mi != hw)) continue;
           if (o.absval) {   // |value| next to an output that keeps the sign: only the first output may be the signed one
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = fabsf(v[j]);
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           else store_direct(o, v, col0, row, b, row_ok);
         }
       }
-      if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + h] = psum;
+      if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
     }
     if (lane == 0) bulk_wait<0>();   // outstanding TMA stores must complete before the CTA's smem goes away
     __syncwarp();

@@ -149,6 +149,29 @@ __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long 
   }
 }
 
+// Osum[n][p] = sum_s (hi + lo)[n*S + s][p] of the token-major occurrence values: grid (P / 32, clips), 8 row groups per block
+__global__ void __launch_bounds__(256) clip_colsum_kernel(const __nv_bfloat16* __restrict__ O, int S, int P, int ld, int lo_off,
+                                                          float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane, n = blockIdx.y;
+  float a = 0.f;
+  if (p < P) {
+    const __nv_bfloat16* base = O + (size_t)n * S * ld + p;
+    for (int s = wy; s < S; s += 8) {
+      a += __bfloat162float(base[(size_t)s * ld]);
+      if (lo_off) a += __bfloat162float(base[(size_t)s * ld + lo_off]);
+    }
+  }
+  red[wy][lane] = a;
+  __syncthreads();
+  if (wy == 0 && p < P) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    out[(size_t)n * P + p] = t;
+  }
+}
+
 // passes of a product of two operands that each come as planes (hi at column 0, lo at column *_lo)
 void set_passes(tcg::Gemm& g, int ex, int a_lo, int b_lo) {
   g.pair = 1;   // CTA pairs wherever the shape allows (tc_gemm.cu decides)
@@ -280,7 +303,9 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   void* occ_user = occ ? reinterpret_cast<char*>(occ) + (size_t)n0 * P * S * elt : nullptr;
   const __nv_bfloat16* pool_a = nullptr;     // pooling A operand
   long long pool_lda = 0;
-  const bool tok_c = p.tok_c && (occ_only || p.w2_first);
+  // W2-after-pooling order: the row sums over s then come from a small column-sum kernel below.  (fp32 maps keep the
+  // per-clip form there: their map leaves as 4-byte plain stores, which measured slower than the TMA rows -- 0.72 vs 0.64 ms)
+  const bool tok_c = p.tok_c && (occ_only || p.w2_first || ex == 1);
   if (tok_c) {
     // few prototypes: O^T = |G2 W5^T| over all tokens in one GEMM (rows = tokens, N = P).  The occurrence map leaves
     // channel-major per clip through plain stores that are coalesced along the voxels; the token-major copy
@@ -302,6 +327,12 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       pool_a = OCC; pool_lda = (long long)ex * p.Pp;
     }
     if ((rc = tcg::launch(g, st))) return rc;
+    if (!occ_only && !p.w2_first) {   // Osum[n][p] = sum_s O[n,s,p] (of the stored values: what the pooling will read)
+      dim3 grid(ceil_div(P, 32), nb);
+      clip_colsum_kernel<<<grid, 256, 0, st>>>(OCC, S, P, ex * p.Pp, ex == 2 ? p.Pp : 0, PSUM);
+      PASN_LAUNCH_CHECK();
+      count_launch();
+    }
   } else {
     tcg::Gemm g{};
     g.A = W5; g.lda = (long long)ex * D2; g.a_batched = 0; g.ka = ex * D2;
@@ -370,6 +401,10 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.b_mn_major = 1; g.b_rows = S;
     g.M = P; g.N = D; g.K = ex == 2 ? p.Sp : S; g.batch = nb; g.bn = D >= 256 ? 256 : 128;
     set_passes(g, ex, p.Sp, 2 * D);
+    if (tok_c) {   // occurrence values token-major: [S rows][P] per clip (MN-major A)
+      g.a_mn_major = 1; g.a_bs = (long long)S * pool_lda; g.ka = ex * p.Pp; g.a_rows = S; g.K = S;
+      set_passes(g, ex, p.Pp, 2 * D);
+    }
     g.act = tcg::ACT_NONE;
     g.out[0] = {POOL, tcg::OUT_BF16_HILO, (long long)2 * D, (long long)P * 2 * D, D};
     if ((rc = tcg::launch(g, st))) return rc;
@@ -382,7 +417,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.M = nb * P; g.N = D; g.K = D; g.batch = 1; g.bn = D >= 256 ? 256 : 128;
     set_passes(g, ex, D, D);
     if (ex == 1) { g.npass = 2; g.a_off[1] = D; }   // pooled = hi + lo planes, W2 bf16
-    g.rowparts = PSUM; g.nparts = 2 * p.tiles_n_c; g.colvec = b2;
+    g.rowparts = PSUM; g.nparts = tok_c ? 1 : 2 * p.tiles_n_c; g.colvec = b2;
     g.act = tcg::ACT_NONE;
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};
     if ((rc = tcg::launch(g, st))) return rc;
