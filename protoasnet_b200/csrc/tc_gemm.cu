@@ -285,29 +285,53 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         ++nstores;
       }
     };
+    // plain stores (unaligned or channel-major outputs).  One tight loop per output mode: with the mode / bounds decided per
+    // element the compiler emitted ~20 instructions per value and this path bounded the GEMMs that use it.
     auto store_direct = [&](const Output& o, const float (&v)[64], int col0, int row, int b, bool row_ok) {
       if (!row_ok) return;
       const int ncols = o.ncols ? o.ncols : g.N;
+      int nv = ncols - col0;            // valid columns of this group
+      if (nv <= 0) return;
+      if (nv > 64) nv = 64;
       // row-major rows, or (trans_S) channel-major per clip with the token index running along the rows of this tile
       const long long base = o.trans_S > 0 ? (long long)(row / o.trans_S) * o.bs + (row % o.trans_S)
                                            : (long long)b * o.bs + (long long)row * o.ld;
       const long long cstep = o.trans_S > 0 ? o.ld : 1;
+      if (o.mode == OUT_F32) {
+        float* p = reinterpret_cast<float*>(o.ptr) + base + (long long)col0 * cstep;
+        if (nv == 64) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int col = col0 + j;
-        if (col >= ncols) continue;
-        const float x = v[j];
-        if (o.mode == OUT_F32) {
-          reinterpret_cast<float*>(o.ptr)[base + col * cstep] = x;
+          for (int j = 0; j < 64; ++j) p[j * cstep] = v[j];
         } else {
-          __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(o.ptr);
-          const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-          p16[base + col * cstep] = hi;
-          if (o.mode == OUT_BF16_HILO) p16[base + o.lo_off + col * cstep] = __float2bfloat16_rn(x - __bfloat162float(hi));
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < nv) p[j * cstep] = v[j];
+        }
+      } else {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(o.ptr) + base + (long long)col0 * cstep;
+        const bool lo = o.mode == OUT_BF16_HILO;
+        if (!lo) {
+          if (nv == 64) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) p[j * cstep] = __float2bfloat16_rn(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (j < nv) p[j * cstep] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          __nv_bfloat16* q = p + o.lo_off;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (j < nv) {
+              const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+              p[j * cstep] = hi;
+              q[j * cstep] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+            }
+          }
         }
       }
     };
-
     // hand an accumulator buffer back to the MMA issuer (of the leader CTA)
     auto acc_release = [&](uint32_t buf) {
       if constexpr (PAIR) {
