@@ -15,6 +15,8 @@
 //   F = W2 H1 + b2 over all tokens, FE[p,:] = sum_s O[p,s] F[:,s] straight out of the pooling GEMM in fp32.
 //   cosine / (.+1)/2 / logits / 1-s / push keys: proto_stage.cu (fp32)
 // Hidden activations are bf16 in HBM between the GEMMs (hi|lo planes in fp32 mode).
+#include <cstdlib>
+
 #include "tc_gemm.cuh"
 
 namespace pasn {
@@ -305,7 +307,8 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   long long pool_lda = 0;
   // W2-after-pooling order: the row sums over s then come from a small column-sum kernel below.  (fp32 maps keep the
   // per-clip form there: their map leaves as 4-byte plain stores, which measured slower than the TMA rows -- 0.72 vs 0.64 ms)
-  const bool tok_c = p.tok_c && (occ_only || p.w2_first || ex == 1);
+  static const int tokc_all = [] { const char* e = getenv("PASN_TOKC_ALL"); return e ? atoi(e) : 0; }();
+  const bool tok_c = p.tok_c && (occ_only || p.w2_first || ex == 1 || tokc_all);
   if (tok_c) {
     // few prototypes: O^T = |G2 W5^T| over all tokens in one GEMM (rows = tokens, N = P).  The occurrence map leaves
     // channel-major per clip through plain stores that are coalesced along the voxels; the token-major copy

@@ -78,6 +78,26 @@ def test_push_bf16_features_match_oracle_indices():
     assert_close(m.prototype_vectors.data, z["new_prototype_vectors"], 4e-3, "prototype_vectors (bf16 mode)")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_push_on_the_tiled_path_matches_oracle(dtype):
+    """Push over image-head feature maps (BASELINE config 2 shape: served by the tiled tensor-core chain, whose prototype
+    stage folds the running argmin and captures the winners) against the oracle's loop: indices exact, vectors close."""
+    dims = synth.CONFIGS["cfg2_image"]
+    bf = dtype == torch.bfloat16
+    sd = synth.make_head_params(dims, seed=77, bias_scale=0.05, bf16_round=bf)
+    n = 120
+    x = synth.make_features(dims, n, seed=13, bf16_round=bf)
+    labels = synth.push_labels(n, dims.K - 1, seed=3)
+    m = build_model(dims, sd)
+    res = pushmod.push_resident(m, torch.from_numpy(x).cuda().to(dtype), torch.from_numpy(labels).cuda(), chunk=50)
+    new, ref_idx, ref_d = po.push_prototypes_oracle(x, labels, sd, dims.K, batch=40, tie_rule="lowest")
+    assert np.array_equal(res["index"].cpu().numpy(), ref_idx)
+    tol = 4e-3 if bf else FP32_RTOL
+    assert_close(res["distance"], ref_d, BF16_RTOL if bf else FP32_RTOL, "winner distances", atol_frac=BF16_RTOL if bf else FP32_RTOL)
+    assert_close(m.prototype_vectors.data, new, tol, "pushed prototype_vectors",
+                 atol_frac=1e-3 if bf else feat_atol(m, torch.from_numpy(x).cuda()))
+
+
 def test_push_ties_break_to_lowest_global_index_and_empty_class():
     dims = synth.CONFIGS["tiny_video"]
     sd = synth.make_head_params(dims, seed=5, bias_scale=0.1)
