@@ -150,9 +150,13 @@ int pasn_occurrence_only(const void* feat, const pasn_weights* w, const void* pa
                          void* occurrence_map, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the head (training: loss.backward() through Video_XProtoNet.forward, src/agents/XProtoNet_Base.py:397,
- * src/agents/Video_XProtoNet_e2e.py:138).  fp32 CUDA-core path; forward intermediates are recomputed, nothing has
- * to be saved by the forward call.  Gradients of the fp32 formulation on the given inputs (a bf16 feature map is read
- * exactly, weights are not rounded); sub-gradients as in PyTorch (relu'(0) = 0, d|x|/dx(0) = 0, clamped norms constant).
+ * src/agents/Video_XProtoNet_e2e.py:138, and through compute_occurence_map, src/loss/loss.py:302).  Forward
+ * intermediates are recomputed, nothing has to be saved by the forward call.  Gradients of the fp32 formulation on the
+ * given inputs (a bf16 feature map is read exactly, weights are not rounded); sub-gradients as in PyTorch (relu'(0) = 0,
+ * d|x|/dx(0) = 0, clamped norms constant).  Shapes the tiled path takes (C % 64 = 0, D % 128 = 0) run on the tensor cores
+ * as three-pass bf16 hi/lo GEMMs (fp32-grade products, fp32 accumulation) unless dims.path is PASN_PATH_GENERIC; the
+ * rest runs on fp32 CUDA-core kernels.  grad_logits = grad_similarity = NULL: only the occurrence branch is recomputed
+ * and differentiated (backward of pasn_occurrence_only); the other parameter gradients are left untouched.
  *   grad_logits      [N,K] fp32 or NULL     grad_similarity [N,P] fp32 or NULL     grad_occurrence [N,P,S] fp32 or NULL
  *   grads            every pointer non-NULL, same shapes as pasn_weights; gradients are ADDED to the buffers
  *   grad_feat        [N,C,S] fp32 (always channel-major, whatever dims.layout says about feat), or NULL           */
