@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) proto_w2_kernel(const K2Params 
   float* s_v = reinterpret_cast<float*>(smem + K2_SM_V);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Ctx ctx{p.err, abort_s, p.fault};
+  Ctx ctx{p.err, abort_s, p.fault, 0};
   if ((smem_u32(smem) & 1023u) != 0) {
     if (tid == 0) atomicCAS(p.err, 0, 901);
     return;
@@ -609,6 +609,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
   static const int x_drain = [] { const char* e = getenv("PASN_X_DRAIN"); return e ? atoi(e) : 0; }();
   k1.x_drain = x_drain;
+  static const int spin = [] { const char* e = getenv("PASN_K1_SPIN"); return e ? atoi(e) : 0; }();
+  k1.spin = spin;
   static const int flush_sleep = [] { const char* e = getenv("PASN_FLUSH_SLEEP"); return e ? atoi(e) : 0; }();
   k1.flush_sleep = flush_sleep;
   static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 0; }();

@@ -51,7 +51,7 @@ static_assert(PASN_XSLOTS != 4 || PASN_WSLOTS != 3 || K1_SMEM <= 195 * 1024, "ke
 
 enum {
   B_XFULL = 0, B_XEMPTY = XSLOTS, B_WFULL = 2 * XSLOTS, B_WEMPTY = 2 * XSLOTS + WSLOTS, B_GDONE = 2 * XSLOTS + 2 * WSLOTS, B_ADONE, B_G1READY, B_G2DONE, B_G2READY, B_ODONE,
-  B_OSREADY, B_OSEMPTY, B_H1TREADY, B_FEDONE0, B_FEFREE0, B_FEDONE1, B_GBFREE, B_ABFREE, B_W4RDY, B_W5RDY, B_COUNT
+  B_OSREADY, B_OSEMPTY, B_H1TREADY, B_FEDONE0, B_FEFREE0, B_FEDONE1, B_GBFREE, B_ABFREE, B_W4RDY, B_W4BRDY, B_W5RDY, B_COUNT
 };
 static_assert(B_COUNT <= 36, "barrier table");
 
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   const int ntok = ncl * S;
   const int ntiles = (ntok + TILE_M - 1) / TILE_M;
   const PackedLayout PL = packed_layout(p.C);
-  Ctx ctx{p.err, abort_s, p.fault};
+  Ctx ctx{p.err, abort_s, p.fault, p.spin};
   const bool two_phase = p.phases != 1;
 
   if ((smem_u32(smem) & 1023u) != 0) {  // swizzled layouts need the 1024-byte alignment we asked for
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
     mbar_init(&bars[B_GBFREE], 8);
     mbar_init(&bars[B_ABFREE], 4);
     mbar_init(&bars[B_W4RDY], 1);
+    mbar_init(&bars[B_W4BRDY], 1);
     mbar_init(&bars[B_W5RDY], 1);
     fence_mbar_init();
   }
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           tc_fence_after();
           stamp(tile, 3);
           for (int kc = 0; kc < nkc && ok; ++kc) {
-            if (kc == a1) ok = pass_w(2, B_W4RDY);
+            if (kc == a1) ok = pass_w(1, B_W4RDY) && pass_w(1, B_W4BRDY);
             if (ok && kc == a2) ok = pass_w(1, B_W5RDY);
             if (!ok) break;
             long long tc0 = 0;
@@ -329,7 +330,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           if (!ok) break;
           mma_commit_a(baddr(B_ADONE));
           stamp(tile, 6);
-          ok = pass_w(2, B_W4RDY) && pass_w(1, B_W5RDY);
+          // the two halves of W4 are handed over one by one: the first eight G2 MMAs only need the first (the stages of
+          // the chain are requested late -- their ring slots free when the last layer-1 blocks retire -- and land ~0.5 k cycles apart)
+          ok = pass_w(1, B_W4RDY) && pass_w(1, B_W4BRDY) && pass_w(1, B_W5RDY);
         }
         if constexpr (TRACE) {
           if (p.trace != nullptr && blockIdx.x == 0 && tile < 16) {
@@ -366,10 +369,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const uint32_t tp = tile & 1;
         const uint32_t base = (uint32_t)tile * stages_per_tile;
         // ---- G2 = G1 W4^T : A from TMEM (cols [0,64) + [192,256)), D = [64,192)
-        if (!(ok = bwait(&bars[B_G1READY], tp, ctx, 104) && bwait(&bars[B_W4RDY], tp, ctx, 113))) break;
+        if (!(ok = bwait(&bars[B_G1READY], tp, ctx, 104))) break;
+        if constexpr (TRACE) K1_TRACE(0, tile, 9);
+        if (!(ok = bwait(&bars[B_W4RDY], tp, ctx, 113))) break;
+        if constexpr (TRACE) K1_TRACE(0, tile, 10);
         tc_fence_after();
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
+          if (st == 1 && !(ok = bwait(&bars[B_W4BRDY], tp, ctx, 115))) break;
           const uint32_t sw = (base + off_w4 + st) % WSLOTS;
           const uint32_t blo = w_lo0 + sw * (WSLOT_BYTES >> 4);
 #pragma unroll
@@ -378,6 +385,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
                      (st | kk) ? 1u : 0u);
           mma_commit_a(baddr(B_WEMPTY) + 8u * sw);
         }
+        if (!ok) break;
         mma_commit_a(baddr(B_G2DONE));
         if constexpr (TRACE) K1_TRACE(0, tile, 4);
         // ---- O = G2 W5^T : A from TMEM (cols [64,96) + [128,160)), D = [0,64)

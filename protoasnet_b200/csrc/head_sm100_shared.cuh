@@ -60,19 +60,24 @@ struct K1Params {
   int l2_hints;                // 1: pooled-vector images are stored evict_last, the feature map is read evict_first
   int flush_sleep;             // ns slept after every fourth prototype row of a clip flush (0: none)
   int x_drain;                 // 1: feature-gather warps publish everything in flight before they block on a full ring
+  int spin;                    // Ctx::spin
 };
 
 struct Ctx {
   int* err;
   volatile int* abort_s;
   int* fault;   // host-mapped sticky fault word (may be null)
+  int spin;     // bit per waiter class (wait code / 100: 1 issuers, 2-3 producers, 4 occurrence warp, 5 epilogue, 6 K2):
+                // poll with test_wait (never suspends) instead of try_wait (may suspend the thread for a while)
 };
 
 // bounded wait: returns false (and raises the CTA-wide abort flag) instead of hanging on a protocol bug.  The spin is
 // out of line so that the fast path at every call site is a single try_wait.
-static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, int* err, volatile int* abort_s, int* fault, int code) {
+static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, int* err, volatile int* abort_s, int* fault, int code,
+                                               int spin) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  const bool poll = (spin >> (code / 100)) & 1;
+  while (!(poll ? mbar_test_wait(bar, parity) : mbar_try_wait(bar, parity))) {
     if (*abort_s) return false;
     if (clock64() - t0 > 4000000000ll) {
       *abort_s = 1;
@@ -85,7 +90,7 @@ static __device__ __noinline__ bool bwait_slow(uint64_t* bar, uint32_t parity, i
 }
 __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, const Ctx& c, int code) {
   if (mbar_try_wait(bar, parity)) return true;
-  return bwait_slow(bar, parity, c.err, c.abort_s, c.fault, code);
+  return bwait_slow(bar, parity, c.err, c.abort_s, c.fault, code, c.spin);
 }
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {

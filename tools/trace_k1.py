@@ -24,7 +24,7 @@ if os.environ.get("PASN_K1_PHASES", "2") == "0":   # first-generation kernel
     names_m = ["start", "tmemfree", "L1issued", "g1ready", "G2issued", "g2ready", "Oissued", "osready", "hs0", "hs1", "poolissued"]
     names_e = ["E-start", "l1done", "E1done", "E2a done", "g2done", "E3done", "odone+osempty", "E4done", "E2b done", "fedone", "E5done"]
 else:                                              # two-phase kernel (head_sm100_k1.cu)
-    names_m = ["start", "gbfree", "Gissued", "abfree", "G2issued", "Oissued", "Aissued", "pool0", "pool1"]
+    names_m = ["start", "gbfree", "Gissued", "abfree", "G2issued", "Oissued", "Aissued", "pool0", "pool1", "g1ready_seen", "w4a_seen"]
     names_e = ["E-start", "gdone", "E1done", "g2done", "E3done", "odone", "E4done", "adone", "E2done", "fedone", "E5done"]
 for tile in range(12):
     if int(t[0, tile, 0]) == 0:
