@@ -423,7 +423,14 @@ def main():
                 "ms_runs_rank0": [round(t, 3) for t in times],
                 "clips_per_sec": n_total / (push_ms * 1e-3), "scaling": "strong",
                 "tensor_frac_of_sustained": f_push / (push_ms * 1e-3) / 1e12 / (world * peaks["bf16_tflops_sustained"]),
-                "winners_sample": idx_ref[:8].tolist(), "collectives_per_push": 1 if world > 1 else 0}
+                "winners_sample": idx_ref[:8].tolist(),
+                # the merge: one kernel over NVLink peer memory (no collective call), or one all-gather of the records
+                "collectives_per_push": 0 if (world == 1 or model.__dict__.get("_pasn_peer_records")
+                                              and any(v is not None for v in model.__dict__["_pasn_peer_records"].values())) else 1,
+                "merge": "single GPU" if world == 1 else
+                         ("one kernel over NVLink peer memory (pasn_push_merge_peers)"
+                          if any(v is not None for v in model.__dict__.get("_pasn_peer_records", {}).values())
+                          else "one NCCL all-gather of [key | vector] records + pasn_push_reduce")}
         model.prototype_vectors.data.copy_(proto0)
         del feats
 

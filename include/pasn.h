@@ -199,6 +199,15 @@ int pasn_push_decode(const uint64_t* best_key, int32_t P, int64_t* index, /* ind
  *   vec[p,:]                            its best_vec row (untouched when !valid)                                  */
 int pasn_push_reduce(const void* gathered, int32_t R, int32_t P, int32_t D, int64_t* index, float* distance, int32_t* valid,
                      float* vec, void* stream);
+/* The merge of a multi-GPU push as ONE kernel over NVLink peer memory instead of a collective call: every rank's record
+ * lives in memory all ranks of the node have mapped (torch symmetric memory in protoasnet_b200/push.py).
+ *   peer_records [R] device array of device pointers to the ranks' records (this rank's own included)
+ *   peer_flags   [R] device array of device pointers to one uint32 epoch flag per rank (zero-initialised, only ever raised)
+ * The kernel publishes this rank's record (system-scope release of `epoch` into its flag), waits (bounded) until every
+ * peer's flag has reached `epoch`, then reduces like pasn_push_reduce, reading keys and the winners' vectors straight
+ * from the peers.  The caller alternates between two record buffers from push to push (epoch parity). */
+int pasn_push_merge_peers(const uint64_t* peer_records, const uint64_t* peer_flags, int32_t R, int32_t my_rank, uint32_t epoch,
+                          int32_t P, int32_t D, int64_t* index, float* distance, int32_t* valid, float* vec, void* stream);
 /* prototype_vectors[p,:] = vec[p,:] where valid[p] != 0 (else unchanged) */
 int pasn_push_write_prototypes(float* prototypes, const float* vec, const int32_t* valid, int32_t P, int32_t D,
                                void* stream);

@@ -255,6 +255,76 @@ __global__ void push_reduce_kernel(const unsigned char* __restrict__ gathered, s
     for (int d = threadIdx.x; d < D; d += blockDim.x) vec[(size_t)p * D + d] = src[d];
   }
 }
+// Exchange + merge of the ranks' push records in ONE kernel over NVLink peer memory (no collective call): every rank's
+// record [keys P x u64 | vectors P x D x f32] lives in memory that all ranks of the node have mapped (symmetric memory).
+// Block p: (block 0 first publishes this rank's record by raising its epoch flag with system scope -- the record was
+// written by earlier kernels of this stream), waits until every peer's flag has reached this push's epoch, reads the R
+// keys of prototype p straight from the peers, keeps the smallest (lowest distance, ties -> lowest global index; equal
+// keys cannot come from different ranks because they carry the global clip index) and copies the winner's vector.
+// Records are double-buffered by epoch parity on the host side, so a rank that starts its next push cannot overwrite
+// a record a slower peer is still reading.  The wait is bounded (fault word), like every wait in this library.
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void __launch_bounds__(128) push_merge_peers_kernel(const unsigned long long* __restrict__ rec_ptrs,
+                                                               const unsigned long long* __restrict__ flag_ptrs, int R, int my_rank,
+                                                               unsigned epoch, int P, int D, int64_t* __restrict__ index,
+                                                               float* __restrict__ distance, int32_t* __restrict__ valid,
+                                                               float* __restrict__ vec, int* fault) {
+  __shared__ long long s_key[64];
+  __shared__ int s_who, s_fail;
+  const int p = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) s_fail = 0;
+  if (blockIdx.x == 0 && tid == 0) {
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<unsigned*>(flag_ptrs[my_rank]), epoch);
+  }
+  __syncthreads();
+  if (tid < R) {
+    const unsigned* f = reinterpret_cast<const unsigned*>(flag_ptrs[tid]);
+    const long long t0 = clock64();
+    // flags only grow; the signed difference tolerates wrap-around of the 32-bit epoch
+    while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+      if (clock64() - t0 > 8000000000ll) {
+        s_fail = 1;
+        if (fault != nullptr) *reinterpret_cast<volatile int*>(fault) = 801;
+        break;
+      }
+      __nanosleep(200);
+    }
+    s_key[tid] = reinterpret_cast<const long long*>(rec_ptrs[tid])[p];
+  }
+  __syncthreads();
+  if (s_fail) return;
+  if (tid == 0) {
+    long long best = 0x7FFFFFFFFFFFFFFFll;
+    int rb = 0;
+    for (int r = 0; r < R; ++r)
+      if (s_key[r] < best) { best = s_key[r]; rb = r; }
+    const unsigned long long key = (unsigned long long)best ^ PASN_KEY_SIGN;
+    const bool ok = key != PASN_KEY_NONE;
+    index[p] = ok ? (long long)(key & 0xFFFFFFFFull) : -1;
+    if (distance) distance[p] = ok ? f32_from_orderable((uint32_t)(key >> 32)) : __int_as_float(0x7f800000);
+    if (valid) valid[p] = ok ? 1 : 0;
+    s_who = ok ? rb : -1;
+  }
+  __syncthreads();
+  if (vec != nullptr) {
+    const int rb = s_who;
+    if (rb >= 0) {
+      const float* src = reinterpret_cast<const float*>(rec_ptrs[rb] + (size_t)P * 8) + (size_t)p * D;
+      for (int d = tid; d < D; d += blockDim.x) vec[(size_t)p * D + d] = __ldcv(src + d);
+    } else {
+      for (int d = tid; d < D; d += blockDim.x) vec[(size_t)p * D + d] = 0.f;
+    }
+  }
+}
+
 __global__ void push_write_kernel(float* protos, const float* vec, const int32_t* valid, int P, int D) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)P * D) return;
@@ -289,6 +359,18 @@ extern "C" int pasn_push_reduce(const void* gathered, int32_t R, int32_t P, int3
   if (((uintptr_t)gathered & 7) != 0) return PASN_ERR_ALIGN;
   push_reduce_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned char*>(gathered),
                                                           pasn_push_record_bytes(P, D), R, P, D, index, distance, valid, vec);
+  PASN_LAUNCH_CHECK();
+  count_launch();
+  return PASN_OK;
+}
+extern "C" int pasn_push_merge_peers(const uint64_t* peer_records, const uint64_t* peer_flags, int32_t R, int32_t my_rank,
+                                     uint32_t epoch, int32_t P, int32_t D, int64_t* index, float* distance, int32_t* valid,
+                                     float* vec, void* stream) {
+  if (!peer_records || !peer_flags || !index || R <= 0 || R > 64 || my_rank < 0 || my_rank >= R || P <= 0 || D <= 0)
+    return PASN_ERR_INVALID;
+  push_merge_peers_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(peer_records),
+                                                                reinterpret_cast<const unsigned long long*>(peer_flags), R, my_rank,
+                                                                epoch, P, D, index, distance, valid, vec, fault_word());
   PASN_LAUNCH_CHECK();
   count_launch();
   return PASN_OK;

@@ -66,9 +66,12 @@ class PushRecord:
     """One rank's running push state in ONE device buffer ``[keys: P x u64 | vectors: P x D x f32]`` (include/pasn.h,
     ``pasn_push_record_bytes``): ``key`` and ``vec`` are views, ``buf`` is what the all-gather moves."""
 
-    def __init__(self, P: int, D: int, device):
+    def __init__(self, P: int, D: int, device, buf: Optional[torch.Tensor] = None):
         self.P, self.D = int(P), int(D)
-        self.buf = torch.zeros(self.P * 8 + self.P * self.D * 4, dtype=torch.uint8, device=device)
+        nbytes = self.P * 8 + self.P * self.D * 4
+        # ``buf``: caller-provided storage (a slice of peer-mapped symmetric memory, see PeerRecords)
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device) if buf is None else buf[:nbytes]
+        self.peer = None   # (PeerRecords, buffer index, epoch) when the merge runs over peer memory
         self.key = self.buf[: self.P * 8].view(torch.int64)
         self.vec = self.buf[self.P * 8:].view(torch.float32).view(self.P, self.D)
         if self.buf.is_cuda:
@@ -78,6 +81,63 @@ class PushRecord:
 
 
 _KEY_NONE = (1 << 63) - 1   # INT64_MAX: no candidate
+
+
+class PeerRecords:
+    """Push records of all ranks of one node in peer-mapped (symmetric) memory, so that the merge is ONE kernel that reads the
+    peers' records over NVLink (``pasn_push_merge_peers``) instead of a collective call.  Per rank: two record buffers
+    (alternating from push to push: a rank that starts its next push never overwrites what a slower peer is still reading)
+    and one epoch flag.  Built once per (model, device, P, D, group): the rendezvous is collective and not cheap."""
+
+    def __init__(self, P: int, D: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.P, self.D = int(P), int(D)
+        rec = self.P * 8 + self.P * self.D * 4
+        self.stride = (rec + 255) // 256 * 256
+        self.mem = symm.empty(2 * self.stride + 256, dtype=torch.uint8, device=device)
+        self.mem.zero_()
+        pg = group if group is not None else dist.group.WORLD
+        self.handle = symm.rendezvous(self.mem, pg)
+        self.rank, self.world = int(self.handle.rank), int(self.handle.world_size)
+        ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        self.rec_ptrs = [torch.tensor([q + b * self.stride for q in ptrs], dtype=torch.int64, device=device) for b in (0, 1)]
+        self.flag_ptrs = torch.tensor([q + 2 * self.stride for q in ptrs], dtype=torch.int64, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)      # every rank's flags are zero before anybody can poll them
+
+    def next_record(self) -> "PushRecord":
+        self.epoch += 1
+        b = self.epoch & 1
+        rec = PushRecord(self.P, self.D, self.mem.device, buf=self.mem[b * self.stride: (b + 1) * self.stride])   # keys reset
+        rec.peer = (self, b, self.epoch)
+        return rec
+
+
+def _peer_records(model, P: int, D: int, device, group=None) -> Optional[PeerRecords]:
+    """PeerRecords for this model (cached), or None when the merge has to go through the all-gather: single rank, CPU
+    bookkeeping, ``PASN_PUSH_PEER=0``, or symmetric memory not available for this group (decided once, by all ranks alike)."""
+    import torch.distributed as dist
+
+    _, world = _world(group)
+    if world == 1 or torch.device(device).type != "cuda" or os.environ.get("PASN_PUSH_PEER", "1") == "0":
+        return None
+    cache = model.__dict__.setdefault("_pasn_peer_records", {})
+    ck = (P, D, str(device), id(group))
+    if ck not in cache:
+        ok = torch.ones(1, dtype=torch.int32, device=device)
+        pr = None
+        try:
+            pr = PeerRecords(P, D, device, group)
+        except Exception as e:   # noqa: BLE001 -- any failure means "use the collective"; all ranks must agree
+            ok.zero_()
+            if os.environ.get("PASN_PUSH_PEER_VERBOSE"):
+                print(f"[protoasnet_b200] peer-memory push merge unavailable: {e!r}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        cache[ck] = pr if int(ok.item()) == 1 else None
+    return cache[ck]
 
 
 def merge_keys(best_key: torch.Tensor, group=None) -> torch.Tensor:
@@ -160,8 +220,22 @@ def finish_push(model, rec: PushRecord, replace_prototypes=True, group=None):
     """One all-gather of the records, per-prototype minimum, prototype overwrite.  No host synchronisation.
     Returns dict(index, distance, features (P,D), valid)."""
     lib = _lib.load()
-    gathered, R = gather_records(rec, group)
-    idx, dmin, valid, vec = reduce_records(gathered, R, rec.P, rec.D)
+    if rec.peer is not None:
+        # exchange + merge in one kernel over NVLink peer memory
+        pr, b, epoch = rec.peer
+        dev = rec.buf.device
+        idx = torch.empty(rec.P, dtype=torch.int64, device=dev)
+        dmin = torch.empty(rec.P, dtype=torch.float32, device=dev)
+        valid = torch.empty(rec.P, dtype=torch.int32, device=dev)
+        vec = torch.empty((rec.P, rec.D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pasn_push_merge_peers(pr.rec_ptrs[b].data_ptr(), pr.flag_ptrs.data_ptr(), pr.world, pr.rank,
+                                                 epoch & 0xFFFFFFFF, rec.P, rec.D, idx.data_ptr(), dmin.data_ptr(),
+                                                 valid.data_ptr(), vec.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                       "pasn_push_merge_peers")
+    else:
+        gathered, R = gather_records(rec, group)
+        idx, dmin, valid, vec = reduce_records(gathered, R, rec.P, rec.D)
     if replace_prototypes:
         pv = model.prototype_vectors.data
         dev = pv.device
@@ -185,7 +259,8 @@ def push_resident(model, features: torch.Tensor, labels: torch.Tensor, global_of
     pc = cache.get(ck)
     if pc is None:
         pc = cache[ck] = proto_class_restriction(model, class_specific, abstain_class).to(dev)
-    rec = PushRecord(P, D, dev)
+    peers = _peer_records(model, P, D, dev, group)
+    rec = peers.next_record() if peers is not None else PushRecord(P, D, dev)
     n_local = features.shape[0]
     for i in range(0, n_local, chunk):
         model.push_scan(features[i:i + chunk], labels[i:i + chunk], pc, global_offset + i, rec.key, backbone=False,
@@ -228,7 +303,8 @@ def push_prototypes(
     dev = model.prototype_vectors.device
     P, D = model.num_prototypes, model.prototype_shape[1]
     pc = proto_class_restriction(model, class_specific, abstain_class).to(dev)
-    rec = PushRecord(P, D, dev)
+    peers = _peer_records(model, P, D, dev, group)
+    rec = peers.next_record() if peers is not None else PushRecord(P, D, dev)
     rank, world = _world(group)
     n_batches = len(dataloader)
     per = -(-n_batches // world)
