@@ -56,6 +56,8 @@ Plan make_plan(const pasn_dims& d) {
                           (size_t)d.P * 2 * p.tiles_n_c * 4 + (size_t)d.P * 2 * d.D * 2 + S * ex * d.D * 2 +
                           (size_t)d.P * d.D * 4 + 2048;
   long long nb = (long long)(((size_t)2 << 30) / per_clip);
+  static const int chunk_env = [] { const char* e = getenv("PASN_TILED_CHUNK"); return e ? atoi(e) : 0; }();   // tests: force chunking
+  if (chunk_env > 0 && nb > chunk_env) nb = chunk_env;
   if (nb < 1) nb = 1;
   if (nb > d.N) nb = d.N > 0 ? d.N : 1;
   p.nb = (int)nb;
@@ -517,6 +519,8 @@ BPlan make_bplan(const pasn_dims& d) {
   const size_t m13 = (size_t)2 * d.D * d.C, m2 = (size_t)d.D * d.D;
   b.part_bytes = align_up((m13 > m2 ? m13 : m2) * 4 * 80, 1024);
   long long nb = (long long)(((size_t)1500 << 20) / per_clip);
+  static const int chunk_env = [] { const char* e = getenv("PASN_TILED_CHUNK"); return e ? atoi(e) : 0; }();
+  if (chunk_env > 0 && nb > chunk_env) nb = chunk_env;
   if (nb < 1) nb = 1;
   if (nb > d.N) nb = d.N > 0 ? d.N : 1;
   b.nb = (int)nb;
