@@ -45,11 +45,20 @@ __global__ void __launch_bounds__(256) proto_rows_reg_kernel(
     for (int i = 0; i < NV; ++i) vq[i] = vq[i] / nv;
   }
   const int pc = best_key != nullptr ? proto_class[p] : 0;
+  // the next row's loads are issued before this row's reductions: a warp walks its rows one after the other, and without
+  // the prefetch each row would pay the full memory latency in front of its dependent shuffle / divide chain
+  float nx[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) nx[i] = __ldcs(feats + (size_t)w0 * D + lane + 32 * i);
   for (long long r = w0; r < rows; r += wstride) {
-    const float* f = feats + (size_t)r * D;
     float a[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) a[i] = __ldcs(f + lane + 32 * i);
+    for (int i = 0; i < NV; ++i) a[i] = nx[i];
+    if (r + wstride < rows) {
+      const float* fn = feats + (size_t)(r + wstride) * D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nx[i] = __ldcs(fn + lane + 32 * i);
+    }
     float ff = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) ff = fmaf(a[i], a[i], ff);

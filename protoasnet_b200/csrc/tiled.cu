@@ -141,6 +141,25 @@ __global__ void __launch_bounds__(256) to_tokens_ncs_kernel(const T* __restrict_
     }
   }
 }
+// small bf16 clips (C*S*2 bytes fit in shared memory, e.g. the 7 x 7 image head): a clip's [C][S] block is one contiguous
+// run in memory, so it is copied in with 16-byte vectors and transposed out of shared memory (rows of S bf16 are not
+// 4-byte aligned, which makes the tiled kernel above read half-empty sectors).  One block per clip.
+__global__ void __launch_bounds__(256) to_tokens_small_bf16_kernel(const __nv_bfloat16* __restrict__ x, int C, int S,
+                                                                   __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(tsm);
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = C * S;                                     // multiple of 8 (host checks): whole 16-byte vectors
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)n * total);
+  for (int i = threadIdx.x; i < total / 8; i += 256) reinterpret_cast<uint4*>(tsm)[i] = __ldg(src + i);
+  __syncthreads();
+  for (int s = warp; s < S; s += 8) {
+    __nv_bfloat16* row = out + ((size_t)n * S + s) * C;
+    for (int c = 2 * lane; c < C; c += 64)
+      *reinterpret_cast<__nv_bfloat162*>(row + c) = __nv_bfloat162(t[c * S + s], t[(c + 1) * S + s]);
+  }
+}
+
 __global__ void to_tokens_nsc_f32_kernel(const float* __restrict__ x, long long rows, int C, __nv_bfloat16* __restrict__ out) {
   const long long n = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -253,8 +272,20 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       to_tokens_nsc_f32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, C, dst);
     } else {
       dim3 grid(ceil_div(S, 32), ceil_div(C, 64), nb);
-      if (ex == 1) to_tokens_ncs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, dst);
-      else to_tokens_ncs_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, dst);
+      const size_t clip_bytes = (size_t)C * S * 2;
+      if (ex == 1 && S < 128 && clip_bytes <= 96 * 1024 && clip_bytes % 16 == 0 && ((uintptr_t)x & 15) == 0) {
+        static bool attr_done = false;
+        if (!attr_done) {
+          if (cudaFuncSetAttribute(to_tokens_small_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+            return PASN_ERR_CUDA;
+          attr_done = true;
+        }
+        to_tokens_small_bf16_kernel<<<nb, 256, clip_bytes, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, dst);
+      } else if (ex == 1) {
+        to_tokens_ncs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), C, S, ex, dst);
+      } else {
+        to_tokens_ncs_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), C, S, ex, dst);
+      }
     }
     PASN_LAUNCH_CHECK();
     count_launch();
