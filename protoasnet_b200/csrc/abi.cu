@@ -168,7 +168,7 @@ extern "C" size_t pasn_head_workspace_bytes(const pasn_dims* dims) {
   size_t need = generic_workspace_bytes(*dims);   // the generic path stays available as the NULL-`packed` fallback
   if (dims->path == PASN_PATH_TCGEN05 || dims->path == PASN_PATH_TILED) need = 0;
   if (fam == FAM_FUSED) { const size_t t = sm100_workspace_bytes(*dims); need = t > need ? t : need; }
-  if (fam == FAM_TILED || (dims->path == PASN_PATH_AUTO && tiled_supported(*dims))) {   // AUTO: occurrence-only may run tiled
+  if (fam == FAM_TILED) {   // (pasn_occurrence_only runs in the same family as the forward)
     const size_t t = tiled_workspace_bytes(*dims);
     need = t > need ? t : need;
   }
