@@ -483,11 +483,12 @@ def main():
         k1_tf = BATCH * flops_clip / (main_ms_avg * 1e-3) / 1e12
         timed_s = ms_step * args.steps * 1e-3
         peak = peaks["bf16_tflops"] if timed_s < 1.0 else peaks["bf16_tflops_sustained"]
-        traffic, traffic_src = None, None
+        traffic, traffic_src, l2sm = None, None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if tc and os.path.exists(tpath):   # dram__bytes_read+write of the dominant kernel from the committed ncu capture
             tj = json.load(open(tpath))
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+            l2sm = tj.get("l2_to_sm_bytes")
         line = {
             "metric": "head_fwd_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -506,7 +507,14 @@ def main():
                          "frac_of_sustained": achieved_tf / peaks["bf16_tflops_sustained"],
                          "frac_k1": k1_tf / peak, "kernel_ms": main_ms_avg, "algorithmic_flop_per_clip": flops_clip,
                          "hbm_gbs": BATCH * bytes_clip / (ms_step * 1e-3) / 1e9,
-                         "hbm_frac": BATCH * bytes_clip / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                         "hbm_frac": BATCH * bytes_clip / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         # what the dominant kernel actually leans on besides the tensor pipe: every SM
+                         # re-streams the layer weights for each 128-voxel tile, L2 -> SM bytes per launch from the same ncu
+                         # capture as `traffic`, over the kernel's live duration and the SM clock sampled during the run
+                         "l2_to_sm": None if not (l2sm and clocks and clocks.get("sm_mhz")) else {
+                             "bytes_per_launch": l2sm, "bytes_per_clk": l2sm / (main_ms_avg * 1e-3 * clocks["sm_mhz"] * 1e6),
+                             "fabric_limit_bytes_per_clk": 6300,
+                             "frac": l2sm / (main_ms_avg * 1e-3 * clocks["sm_mhz"] * 1e6) / 6300.0}},
             "sustained": sustained,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "push": push,
             "channels_last": channels_last,
