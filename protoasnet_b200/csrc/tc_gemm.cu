@@ -16,6 +16,12 @@
 // with remote arrivals.  Per flop a pair pulls 2/3 of the bytes from L2 that two independent CTAs would (the chain's big
 // GEMMs are bound by the ~6300 B/clk L2 -> SM fabric, not by the tensor pipe: profiles/README.md).
 //
+// MODE 2 ("quad") puts two such pairs in one 4-CTA cluster on M-adjacent 256-row tiles.  They need the same B tile, so each of
+// the four CTAs loads a quarter of it and the TMA unit multicasts it into the CTA of the other pair that holds the same
+// half: per 64-deep k-block a CTA then pulls 16 + 8 KB through the L2 -> SM fabric instead of 16 + 16 (the long-K GEMMs
+// run exactly at that fabric's limit).  A stage may only be refilled once BOTH pairs have consumed it: their commits
+// arrive on the "stage free" barriers of all four CTAs.  Opt-in (PASN_GEMM_QUAD=1): measured slower than plain pairs.
+//
 // Every mbarrier wait is bounded: a protocol fault becomes an error code in *err, not a hung GPU.
 #include <cuda.h>
 
@@ -65,6 +71,15 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar) & 0xFEFFFFFFu)
       : "memory");
 }
+// ... and multicast: the box lands at the same shared-memory offset in every CTA of `mask`, the bytes are counted on the
+// barrier of each destination CTA's pair leader
+__device__ __forceinline__ void tma_load_3d_2sm_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
                "r"(c1), "r"(c2), "r"(src)
@@ -95,8 +110,9 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, 
 
 }  // namespace
 
-template <bool PAIR>
+template <int MODE>   // 0: one CTA per tile, 1: CTA pairs, 2: two pairs per cluster sharing the B tile by multicast
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ KParams kp) {
+  constexpr bool PAIR = MODE >= 1, QUAD = MODE == 2;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
@@ -106,9 +122,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (tid == 0) *reinterpret_cast<volatile int*>(kp.err) = 700;
     return;
   }
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;         // rank in the cluster
+  const uint32_t rank = crank & 1u;                             // rank in the pair: 0 = leader
+  const uint32_t pq = crank >> 1;                               // pair inside a quad
   if (tid == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], QUAD ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_ACCFULL + i], 1); mbar_init(&bars[B_ACCEMPTY + i], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     fence_mbar_init();
     prefetch_tmap(&kp.tmA);
@@ -125,9 +143,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   const int bnl = PAIR ? bn / 2 : bn;                           // rows of the B tile this CTA loads
   const int tiles_per_batch = kp.tiles_m * kp.tiles_n;
   const int ntiles = g.batch * tiles_per_batch;
-  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent walk of this CTA / pair
-  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int BMT = PAIR ? 2 * BM : BM;                                   // rows of a (pair) tile
+  constexpr int CL = QUAD ? 4 : (PAIR ? 2 : 1);                             // CTAs per cluster = per tile
+  const int tile0 = (int)(blockIdx.x / CL);                                 // persistent walk of this CTA / pair / quad
+  const int tstep = (int)(gridDim.x / CL);
+  constexpr int BMT = CL * BM;                                              // rows of a (cluster) tile
+  constexpr int BMP = PAIR ? 2 * BM : BM;                                   // rows of one MMA (a pair's share)
+  const uint16_t pair_mask = (uint16_t)(3u << (2u * pq));                   // the two CTAs of this pair
   const uint32_t stage_bytes = A_BYTES + (uint32_t)bnl * 128u;              // multiple of 1024: swizzle atoms stay aligned
   const uint32_t nst_fit = (STAGES * STAGE_BYTES) / stage_bytes;
   const uint32_t nst = nst_fit < (uint32_t)MAX_STAGES ? nst_fit : (uint32_t)MAX_STAGES;
@@ -144,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       };
       for (int t = tile0; t < ntiles && ok; t += tstep) {
         const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
-        const int m0 = (r / kp.tiles_n) * BMT + (int)rank * BM, n0 = (r % kp.tiles_n) * bn + (int)rank * bnl;
+        const int m0 = (r / kp.tiles_n) * BMT + (int)pq * BMP + (int)rank * BM, n0 = (r % kp.tiles_n) * bn + (int)rank * bnl;
         const bool split_k = g.k_rows_per_batch > 0;
         const int krow0 = split_k ? b * g.k_rows_per_batch : 0;
         for (int pass = 0; pass < g.npass && ok; ++pass) {
@@ -160,7 +181,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 tma_load(dst + j * 8192, &kp.tmA, g.a_off[pass] + m0 + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
                          &bars[B_FULL + s]);
             }
-            if (!g.b_mn_major) {
+            if constexpr (QUAD) {
+              // this CTA's half of the B tile (128 rows) is also the half of the CTA with the same pair rank in the other
+              // pair: each of the two loads 64 of its rows and multicasts them to both (bn = 256 only)
+              const uint16_t mc = (uint16_t)((1u << rank) | (1u << (rank + 2u)));
+              if (!g.b_mn_major)
+                tma_load_3d_2sm_mc(dst + A_BYTES + pq * 8192u, &kp.tmB, g.b_off[pass] + kb * BK, n0 + 64 * (int)pq, g.b_batched ? b : 0,
+                                   &bars[B_FULL + s], mc);
+              else
+                tma_load_3d_2sm_mc(dst + A_BYTES + pq * 8192u, &kp.tmB, g.b_off[pass] + n0 + 64 * (int)pq, krow,
+                                   (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s], mc);
+            } else if (!g.b_mn_major) {
               tma_load(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
             } else {
               for (int j = 0; j < bnl / 64; ++j)
@@ -176,14 +207,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   } else if (warp == 1 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
     if (elect_one()) {
-      const uint32_t id = make_idesc_16(BMT, (uint32_t)bn, 1u, 1u, g.a_mn_major ? 1u : 0u, g.b_mn_major ? 1u : 0u);
+      const uint32_t id = make_idesc_16(BMP, (uint32_t)bn, 1u, 1u, g.a_mn_major ? 1u : 0u, g.b_mn_major ? 1u : 0u);
       auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t acc) {
         if constexpr (PAIR) mma_ss2_x(d, alo, ahi, blo, bhi, id, acc);
         else mma_ss_x(d, alo, ahi, blo, bhi, id, acc);
       };
-      auto commit = [&](uint32_t bar_saddr) {
-        if constexpr (PAIR) mma_commit2_a(bar_saddr, (uint16_t)3);
+      auto commit = [&](uint32_t bar_saddr) {          // to this pair
+        if constexpr (PAIR) mma_commit2_a(bar_saddr, pair_mask);
         else mma_commit_a(bar_saddr);
+      };
+      auto commit_stage = [&](uint32_t bar_saddr) {    // "stage free": in a quad, to all four CTAs (both pairs refill each other)
+        if constexpr (QUAD) mma_commit2_a(bar_saddr, (uint16_t)0xF);
+        else commit(bar_saddr);
       };
       const uint32_t a_lbo = g.a_mn_major ? 8192u : 16u, a_kstep = g.a_mn_major ? 128u : 2u;
       constexpr uint32_t HI = desc_hi(1024, SWZ_128B);
@@ -205,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + A_BYTES, b_lbo);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) mma(d, alo + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, (pass | kb | k4) ? 1u : 0u);
-            commit(bar0 + 8u * (B_EMPTY + s));
+            commit_stage(bar0 + 8u * (B_EMPTY + s));
             s = s + 1 == nst ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
           }
@@ -335,14 +370,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     // hand an accumulator buffer back to the MMA issuer (of the leader CTA)
     auto acc_release = [&](uint32_t buf) {
       if constexpr (PAIR) {
-        if (rank != 0) { mbar_arrive_cluster(mapa_u32(smem_u32(&bars[B_ACCEMPTY + buf]), 0)); return; }
+        if (rank != 0) { mbar_arrive_cluster(mapa_u32(smem_u32(&bars[B_ACCEMPTY + buf]), crank & ~1u)); return; }
       }
       mbar_arrive(&bars[B_ACCEMPTY + buf]);
     };
     for (int t = tile0; t < ntiles && ok; t += tstep, ++i) {
       const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
       const int tn = r % kp.tiles_n;
-      const int m0 = (r / kp.tiles_n) * BMT + (int)rank * BM, n0 = tn * bn;
+      const int m0 = (r / kp.tiles_n) * BMT + (int)pq * BMP + (int)rank * BM, n0 = tn * bn;
       const uint32_t buf = i & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -544,8 +579,9 @@ int launch(const Gemm& g, cudaStream_t st) {
   if (g.npass < 1 || g.npass > 4 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return PASN_ERR_CUDA;
     attr_done = true;
   }
@@ -553,12 +589,19 @@ int launch(const Gemm& g, cudaStream_t st) {
   // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py); short-K GEMMs are bound by
   // their epilogues and lose a little to the cross-CTA hand-offs
   const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= 8)) && g.bn >= 128 && g.M > BM;
+  // two pairs per cluster sharing the B tile by multicast (full-width tiles, at least two pair tiles along M).  Correct (unit
+  // tests with PASN_GEMM_PAIR=1 PASN_GEMM_QUAD=1) but measured SLOWER than plain pairs -- 8192^3: 694 vs 1264 TFLOP/s, layer-1
+  // shape 602 vs 1005: the stage hand-back needs both pairs' commits and the 4-deep ring cannot cover the extra cluster
+  // round trip -- so it is opt-in only.
+  static const int quad_env = [] { const char* e = getenv("PASN_GEMM_QUAD"); return e ? atoi(e) : 0; }();
+  const bool quad = pair && quad_env != 0 && g.bn == 256 && g.M > 2 * BM;
+  const int cl = quad ? 4 : (pair ? 2 : 1);
   int* fault = fault_word();   // bounded waits report into the host-mapped sticky fault word
   if (fault == nullptr) return PASN_ERR_CUDA;
   KParams kp;
   kp.g = g;
   kp.err = fault;
-  kp.tiles_m = ceil_div(g.M, pair ? 2 * BM : BM);
+  kp.tiles_m = ceil_div(g.M, cl * BM);
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);
   const bool split_k = g.k_rows_per_batch > 0;
@@ -575,7 +618,7 @@ int launch(const Gemm& g, cudaStream_t st) {
   }
   if (!g.b_mn_major) {
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
-                  (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)(pair ? g.bn / 2 : g.bn)))
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.N), g.b_batched ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, BK, (unsigned)(quad ? 64 : (pair ? g.bn / 2 : g.bn))))
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
@@ -608,16 +651,17 @@ int launch(const Gemm& g, cudaStream_t st) {
   const long long ntiles = (long long)g.batch * kp.tiles_m * kp.tiles_n;
   if (!pair) {
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    tc_gemm_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(kp);
+    tc_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(kp);
   } else {
-    const int npairs = (int)(ntiles < num_sms / 2 ? ntiles : num_sms / 2);
+    const int ncl = (int)(ntiles < num_sms / cl ? ntiles : num_sms / cl);   // clusters of 2 (pair) or 4 (quad) CTAs
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(cl * ncl); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, kp) != cudaSuccess) return PASN_ERR_CUDA;
+    const cudaError_t e = quad ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, kp);
+    if (e != cudaSuccess) return PASN_ERR_CUDA;
   }
   PASN_LAUNCH_CHECK();
   count_launch();
