@@ -54,6 +54,7 @@ struct alignas(64) KParams {
   CUtensorMap tmA, tmB, tmO[4];   // out0 (hi), out0 lo, out1 (hi), out1 lo
   Gemm g;
   int out_tma[2];
+  int tall;   // 1: a tile has two 128-row (per CTA) sub-tiles that share each B stage; they take the two accumulator buffers
   int tiles_m, tiles_n, nkb;
   int* err;
 };
@@ -146,10 +147,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   constexpr int CL = QUAD ? 4 : (PAIR ? 2 : 1);                             // CTAs per cluster = per tile
   const int tile0 = (int)(blockIdx.x / CL);                                 // persistent walk of this CTA / pair / quad
   const int tstep = (int)(gridDim.x / CL);
-  constexpr int BMT = CL * BM;                                              // rows of a (cluster) tile
   constexpr int BMP = PAIR ? 2 * BM : BM;                                   // rows of one MMA (a pair's share)
+  constexpr int BMC = CL * BM;                                              // rows of one sub-tile across the cluster
+  const int nu = kp.tall ? 2 : 1;                                           // sub-tiles per tile (long-K GEMMs: see launch())
+  const int BMT = BMC * nu;                                                 // rows of a (cluster) tile
   const uint16_t pair_mask = (uint16_t)(3u << (2u * pq));                   // the two CTAs of this pair
-  const uint32_t stage_bytes = A_BYTES + (uint32_t)bnl * 128u;              // multiple of 1024: swizzle atoms stay aligned
+  const uint32_t a_stage = A_BYTES * (uint32_t)nu;                          // A boxes of a stage (one per sub-tile)
+  const uint32_t stage_bytes = a_stage + (uint32_t)bnl * 128u;              // multiple of 1024: swizzle atoms stay aligned
   const uint32_t nst_fit = (STAGES * STAGE_BYTES) / stage_bytes;
   const uint32_t nst = nst_fit < (uint32_t)MAX_STAGES ? nst_fit : (uint32_t)MAX_STAGES;
 
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (elect_one()) {
       uint32_t s = 0, ph = 0;
       bool ok = true;
-      const uint32_t stage_tx = (A_BYTES + (uint32_t)bnl * 128u) * (PAIR ? 2u : 1u);   // both CTAs' bytes land on the leader's barrier
+      const uint32_t stage_tx = stage_bytes * (PAIR ? 2u : 1u);   // both CTAs' bytes land on the leader's barrier
       auto tma_load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
         if constexpr (PAIR) tma_load_3d_2sm(dst, map, c0, c1, c2, bar);
         else tma_load_3d(dst, map, c0, c1, c2, bar);
@@ -174,28 +178,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const uint32_t dst = sbase + s * stage_bytes;
             if (rank == 0) mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
             const int krow = krow0 + kb * BK;   // K coordinate of MN-major operands (rows)
-            if (!g.a_mn_major) {
-              tma_load(dst, &kp.tmA, g.a_off[pass] + kb * BK, m0, g.a_batched ? b : 0, &bars[B_FULL + s]);
-            } else {
-              for (int j = 0; j < 2; ++j)
-                tma_load(dst + j * 8192, &kp.tmA, g.a_off[pass] + m0 + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
-                         &bars[B_FULL + s]);
+            for (int u = 0; u < nu; ++u) {
+              const int mu = m0 + u * BMC;
+              const uint32_t da = dst + (uint32_t)u * A_BYTES;
+              if (!g.a_mn_major) {
+                tma_load(da, &kp.tmA, g.a_off[pass] + kb * BK, mu, g.a_batched ? b : 0, &bars[B_FULL + s]);
+              } else {
+                for (int j = 0; j < 2; ++j)
+                  tma_load(da + j * 8192, &kp.tmA, g.a_off[pass] + mu + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
+                           &bars[B_FULL + s]);
+              }
             }
             if constexpr (QUAD) {
               // this CTA's half of the B tile (128 rows) is also the half of the CTA with the same pair rank in the other
               // pair: each of the two loads 64 of its rows and multicasts them to both (bn = 256 only)
               const uint16_t mc = (uint16_t)((1u << rank) | (1u << (rank + 2u)));
               if (!g.b_mn_major)
-                tma_load_3d_2sm_mc(dst + A_BYTES + pq * 8192u, &kp.tmB, g.b_off[pass] + kb * BK, n0 + 64 * (int)pq, g.b_batched ? b : 0,
+                tma_load_3d_2sm_mc(dst + a_stage + pq * 8192u, &kp.tmB, g.b_off[pass] + kb * BK, n0 + 64 * (int)pq, g.b_batched ? b : 0,
                                    &bars[B_FULL + s], mc);
               else
-                tma_load_3d_2sm_mc(dst + A_BYTES + pq * 8192u, &kp.tmB, g.b_off[pass] + n0 + 64 * (int)pq, krow,
+                tma_load_3d_2sm_mc(dst + a_stage + pq * 8192u, &kp.tmB, g.b_off[pass] + n0 + 64 * (int)pq, krow,
                                    (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s], mc);
             } else if (!g.b_mn_major) {
-              tma_load(dst + A_BYTES, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
+              tma_load(dst + a_stage, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
             } else {
               for (int j = 0; j < bnl / 64; ++j)
-                tma_load(dst + A_BYTES + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
+                tma_load(dst + a_stage + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
                          (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s]);
             }
             s = s + 1 == nst ? 0 : s + 1;
@@ -227,9 +235,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       uint32_t s = 0, ph = 0;
       bool ok = true;
       int i = 0;
-      for (int t = tile0; t < ntiles && ok; t += tstep, ++i) {
+      // i counts sub-tiles (= accumulator hand-overs); a tall tile takes both buffers at once
+      for (int t = tile0; t < ntiles && ok; t += tstep, i += nu) {
         const uint32_t buf = i & 1;
         if (!(ok = bwait(&bars[B_ACCEMPTY + buf], ((i >> 1) & 1) ^ 1, kp.err, 711))) break;
+        if (nu == 2 && !(ok = bwait(&bars[B_ACCEMPTY + 1], ((i >> 1) & 1) ^ 1, kp.err, 713))) break;
         tc_fence_after();
         const uint32_t d = tbase + 256u * buf;
         for (int pass = 0; pass < g.npass && ok; ++pass) {
@@ -237,15 +247,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
             tc_fence_after();
             const uint32_t sa = sbase + s * stage_bytes;
-            const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + A_BYTES, b_lbo);
+            const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + a_stage, b_lbo);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) mma(d, alo + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, (pass | kb | k4) ? 1u : 0u);
+            if (nu == 2) {   // second sub-tile: its own A box, the same B stage, the other accumulator buffer
+              const uint32_t alo1 = desc_lo(sa + A_BYTES, a_lbo);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                mma(tbase + 256u, alo1 + k4 * a_kstep, HI, blo + k4 * b_kstep, HI, (pass | kb | k4) ? 1u : 0u);
+            }
             commit_stage(bar0 + 8u * (B_EMPTY + s));
             s = s + 1 == nst ? 0 : s + 1;
             ph ^= (s == 0) ? 1u : 0u;
           }
         }
-        if (ok) commit(bar0 + 8u * (B_ACCFULL + buf));
+        if (ok) {
+          commit(bar0 + 8u * (B_ACCFULL + buf));
+          if (nu == 2) commit(bar0 + 8u * (B_ACCFULL + 1));
+        }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -374,10 +393,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       }
       mbar_arrive(&bars[B_ACCEMPTY + buf]);
     };
-    for (int t = tile0; t < ntiles && ok; t += tstep, ++i) {
+    for (int tv = 0; ok; ++tv, ++i) {       // sub-tiles in the issuer's order: tile tile0 + (tv / nu) * tstep, sub-tile tv % nu
+      const int t = tile0 + (tv / nu) * tstep;
+      if (t >= ntiles) break;
       const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
       const int tn = r % kp.tiles_n;
-      const int m0 = (r / kp.tiles_n) * BMT + (int)pq * BMP + (int)rank * BM, n0 = tn * bn;
+      const int m0 = (r / kp.tiles_n) * BMT + (tv % nu) * BMC + (int)pq * BMP + (int)rank * BM, n0 = tn * bn;
       const uint32_t buf = i & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < g.M;
@@ -596,12 +617,18 @@ int launch(const Gemm& g, cudaStream_t st) {
   static const int quad_env = [] { const char* e = getenv("PASN_GEMM_QUAD"); return e ? atoi(e) : 0; }();
   const bool quad = pair && quad_env != 0 && g.bn == 256 && g.M > 2 * BM;
   const int cl = quad ? 4 : (pair ? 2 : 1);
+  // tall tiles for long main loops: two sub-tiles per CTA share every B stage (and take both accumulator buffers, so the
+  // epilogue no longer overlaps the MMAs -- negligible when K is long): a quarter less L2 -> SM traffic per flop
+  static const int tall_env = [] { const char* e = getenv("PASN_GEMM_TALL"); return e ? atoi(e) : -1; }();
+  const bool tall = pair && !quad && g.M > cl * BM &&
+                    (tall_env >= 0 ? tall_env != 0 : ceil_div(g.K, BK) * g.npass >= 40);   // (24 k-block passes: 285 vs 267 us, slower)
   int* fault = fault_word();   // bounded waits report into the host-mapped sticky fault word
   if (fault == nullptr) return PASN_ERR_CUDA;
   KParams kp;
   kp.g = g;
   kp.err = fault;
-  kp.tiles_m = ceil_div(g.M, cl * BM);
+  kp.tall = tall ? 1 : 0;
+  kp.tiles_m = ceil_div(g.M, cl * BM * (tall ? 2 : 1));
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);
   const bool split_k = g.k_rows_per_batch > 0;
