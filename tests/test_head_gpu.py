@@ -253,13 +253,13 @@ TILED_SHAPES = [
     (192, 128, 8, 2, (2, 10, 12), 7),     # S = 240 > 2P: W2 after the pooling (row sums, rank-1 bias term)
     (512, 512, 40, 4, (7, 7), 11),        # the image head
     (64, 128, 72, 4, (4, 16, 16), 2),     # P > 64: occurrence GEMM per clip, S = 1024 (aligned: no transposition in bf16)
-    (64, 128, 16, 4, (8,), 1),            # a single tiny clip (sequence-like [N,C,L] is not a valid map: goes through ndim check)
+    (128, 256, 40, 4, (1, 2, 4), 1),      # a single clip of 8 voxels: every GEMM is one ragged tile
 ]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("layout", ["ncs", "nsc"])
-@pytest.mark.parametrize("shape", TILED_SHAPES[:-1], ids=[str(s) for s in TILED_SHAPES[:-1]])
+@pytest.mark.parametrize("shape", TILED_SHAPES, ids=[str(s) for s in TILED_SHAPES])
 def test_tiled_path_shape_sweep(shape, layout, dtype):
     """The tiled tensor-core chain (explicitly requested) on ragged shapes, both layouts and dtypes, against the CPU oracle."""
     C, D, P, K, spatial, n = shape
@@ -280,7 +280,9 @@ def test_tiled_path_shape_sweep(shape, layout, dtype):
     assert torch.equal(out["distance"], 1 - out["similarity"])
     assert torch.equal(out["logits"], out["logits2"])
     if bf:
-        assert_close(out["features_extracted"], rf.numpy(), 4e-3, "features_extracted", atol_frac=1e-3)
+        # bf16 hidden activations (2^-9 relative each) are averaged over the S voxels of a clip: the fewer voxels, the
+        # more of that rounding is left in the pooled features (north_star's 1e-3 bound is on similarities / logits, above)
+        assert_close(out["features_extracted"], rf.numpy(), 4e-3, "features_extracted", atol_frac=max(1e-3, 6e-3 / dims.S ** 0.5))
         for k in ("occurrence_map", "occ2", "occ3"):
             assert_close(out[k], ro.numpy(), 2e-2, k, atol_frac=1e-2)
     else:
