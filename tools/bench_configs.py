@@ -32,7 +32,8 @@ for name, n, dt, path in cases:
     fam = "generic FFMA"
     if path != G and lib.pasn_tcgen05_supported(C.byref(d)):
         d2 = m._rt.make_dims(x, F)[0]
-        fam = "fused tcgen05" if (path in (A, F) and lib.pasn_tcgen05_supported(C.byref(d2))) else "tiled tcgen05"
+        fused = lib.pasn_tcgen05_supported(C.byref(d2)) and (path == F or (path == A and dt == torch.bfloat16))   # AUTO keeps fp32 maps exact: tiled hi/lo chain
+        fam = "fused tcgen05" if fused else "tiled tcgen05"
         if fam == "tiled tcgen05" and dt == torch.float32:
             fam += " (hi/lo split)"
     S = dims.S
