@@ -54,6 +54,11 @@ __device__ __forceinline__ void key_atomic_min_global(unsigned long long* best_k
   atomicMin(reinterpret_cast<long long*>(best_key_signed), (long long)(key_u ^ PASN_KEY_SIGN));
 }
 
+// programmatic dependent launch (see launch_pdl): let the next kernel of the stream start setting itself up / wait until the
+// kernel in front has completed and flushed its writes.  Both are no-ops for a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -63,6 +68,19 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with programmatic stream serialization allowed: the kernel may be scheduled while
+// the previous kernel of the stream drains; it must call pdl_wait() before its first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- generic path (generic.cu) -------------------------------------------------------------

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256) proto_rows_reg_kernel(
     float* __restrict__ sim, float* __restrict__ dist, const int64_t* __restrict__ labels,
     const int32_t* __restrict__ proto_class, long long global_offset, unsigned long long* __restrict__ best_key) {
   constexpr int D = NV * 32;
+  pdl_launch_dependents();
+  pdl_wait();   // the features come from the kernel in front (pooling / W2 GEMM)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long w0 = (long long)blockIdx.x * 8 + warp, wstride = (long long)gridDim.x * 8;   // wstride % P == 0 (host)
   if (w0 >= rows) return;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(PS_THREADS) proto_rows_kernel(
 __global__ void __launch_bounds__(PS_THREADS) proto_logits_kernel(const float* __restrict__ sim,
                                                                   const float* __restrict__ last_layer, int N, int P, int K,
                                                                   float* __restrict__ logits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     const float* s = sim + (size_t)n * P;
@@ -147,6 +151,8 @@ __global__ void __launch_bounds__(PS_THREADS) proto_logits_wide_kernel(const flo
                                                                        const float* __restrict__ last_layer, int N, int P, int K,
                                                                        float* __restrict__ logits) {
   __shared__ float red[PS_WARPS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x / K, k = blockIdx.x - n * K;
   const float* s = sim + (size_t)n * P;
@@ -194,10 +200,12 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
     long long warps = per * m;
     while (warps % 8 != 0) warps += per;                 // at most 7 steps; stays a multiple of P
     const unsigned blocks = (unsigned)(warps / 8);
-    if (D == 128) proto_rows_reg_kernel<4><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
-    else if (D == 256) proto_rows_reg_kernel<8><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
-    else if (D == 512) proto_rows_reg_kernel<16><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
-    else proto_rows_reg_kernel<32><<<blocks, 256, 0, st>>>(feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    cudaError_t e;
+    if (D == 128) e = launch_pdl(proto_rows_reg_kernel<4>, dim3(blocks), dim3(256), 0, st, feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else if (D == 256) e = launch_pdl(proto_rows_reg_kernel<8>, dim3(blocks), dim3(256), 0, st, feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else if (D == 512) e = launch_pdl(proto_rows_reg_kernel<16>, dim3(blocks), dim3(256), 0, st, feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    else e = launch_pdl(proto_rows_reg_kernel<32>, dim3(blocks), dim3(256), 0, st, feats, protos, rows, P, sim, dist, labels, pcls, goff, bkey);
+    if (e != cudaSuccess) return PASN_ERR_CUDA;
   } else {
     long long blocks = (rows + PS_WARPS - 1) / PS_WARPS;
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -205,10 +213,12 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
   }
   PASN_LAUNCH_CHECK();
   count_launch();
-  if (P >= 1024 && (long long)N * K <= 148 * 64)
-    proto_logits_wide_kernel<<<N * K, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
-  else
-    proto_logits_kernel<<<N < 148 * 8 ? N : 148 * 8, PS_THREADS, 0, st>>>(sim, last_layer, N, P, K, logits);
+  if (P >= 1024 && (long long)N * K <= 148 * 64) {
+    if (launch_pdl(proto_logits_wide_kernel, dim3(N * K), dim3(PS_THREADS), 0, st, sim, last_layer, N, P, K, logits) != cudaSuccess) return PASN_ERR_CUDA;
+  } else {
+    if (launch_pdl(proto_logits_kernel, dim3(N < 148 * 8 ? N : 148 * 8), dim3(PS_THREADS), 0, st, sim, last_layer, N, P, K, logits) != cudaSuccess)
+      return PASN_ERR_CUDA;
+  }
   PASN_LAUNCH_CHECK();
   count_launch();
   if (push && push->best_vec) {   // winner capture in the same pass (push_abs_revision.py:299-302)

@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrival / multicast commit
   tc_fence_after();
+  // programmatic dependent launch: the chain's GEMMs follow each other on one stream; the next launch may set itself up
+  // (barriers, TMEM, tensor-map prefetch) while this grid drains, and nothing here touches global memory before the
+  // grid in front of it has completed
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t sbase = smem_u32(smem);
   const int bn = g.bn;
@@ -676,18 +681,26 @@ int launch(const Gemm& g, cudaStream_t st) {
     return n;
   }();
   const long long ntiles = (long long)g.batch * kp.tiles_m * kp.tiles_n;
-  if (!pair) {
-    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    tc_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(kp);
-  } else {
-    const int ncl = (int)(ntiles < num_sms / cl ? ntiles : num_sms / cl);   // clusters of 2 (pair) or 4 (quad) CTAs
+  {
+    static const int pdl_env = [] { const char* e = getenv("PASN_GEMM_PDL"); return e ? atoi(e) : 1; }();
+    const int ncl = (int)(ntiles < num_sms / cl ? ntiles : num_sms / cl);   // clusters of 1, 2 (pair) or 4 (quad) CTAs
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cl * ncl); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    const cudaError_t e = quad ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, kp);
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (cl > 1) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = cl; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_env) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    const cudaError_t e = quad ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, kp)
+                               : (pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0>, kp));
     if (e != cudaSuccess) return PASN_ERR_CUDA;
   }
   PASN_LAUNCH_CHECK();
