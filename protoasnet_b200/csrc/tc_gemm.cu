@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const float* rp = g.rowparts + ((size_t)b * g.M + row) * g.nparts;
         for (int j = 0; j < g.nparts; ++j) rowterm += rp[j];
       }
-      float psum = 0.f;
+      float psum = 0.f, st_ff = 0.f, st_dot = 0.f;
       if (has_vec && h < nh && m0 + q * 32 < g.M) {   // bias / colvec slices of this warp's groups -> per-warp smem, before the accumulator is due
         __syncwarp();
         for (int cg = 0; cg < ngroups; ++cg) {
@@ -434,6 +434,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         __syncwarp();
         if (lane == 0) acc_release(buf);
         if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = 0.f;
+        if (g.rowstat != nullptr && row_ok)
+          *reinterpret_cast<float2*>(g.rowstat + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) = make_float2(0.f, 0.f);
         continue;
       }
       for (int cg = 0; cg < ngroups; ++cg) {
@@ -519,6 +521,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if (mk) apply_bf16(mk, mcs, false);
           }
         }
+        if (g.rowstat != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
+          const float* vr = g.dotvec + (long long)(row % g.dot_mod) * g.dot_ld + col0;
+          if (col0 + 64 <= g.N && ((reinterpret_cast<uintptr_t>(vr) & 15) == 0)) {
+#pragma unroll
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(vr) + j4);
+              st_ff = fmaf(v[4 * j4], v[4 * j4], st_ff);         st_dot = fmaf(v[4 * j4], w4.x, st_dot);
+              st_ff = fmaf(v[4 * j4 + 1], v[4 * j4 + 1], st_ff); st_dot = fmaf(v[4 * j4 + 1], w4.y, st_dot);
+              st_ff = fmaf(v[4 * j4 + 2], v[4 * j4 + 2], st_ff); st_dot = fmaf(v[4 * j4 + 2], w4.z, st_dot);
+              st_ff = fmaf(v[4 * j4 + 3], v[4 * j4 + 3], st_ff); st_dot = fmaf(v[4 * j4 + 3], w4.w, st_dot);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < g.N) { st_ff = fmaf(v[j], v[j], st_ff); st_dot = fmaf(v[j], __ldg(vr + j), st_dot); }
+          }
+        }
         if (g.psum != nullptr) {
           if (col0 + 64 <= g.N) {
             if (g.psum_rounded) {
@@ -547,6 +566,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         }
       }
       if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
+      if (g.rowstat != nullptr && row_ok)
+        *reinterpret_cast<float2*>(g.rowstat + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) =
+            (split_out && hw == 1) ? make_float2(0.f, 0.f) : make_float2(st_ff, st_dot);
     }
     if (lane == 0) bulk_wait<0>();   // outstanding TMA stores must complete before the CTA's smem goes away
     __syncwarp();

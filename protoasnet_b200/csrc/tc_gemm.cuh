@@ -58,6 +58,10 @@ struct Gemm {
   int psum_rounded;              // ... of the bf16-rounded values (what a bf16 consumer of out[0] will read) or of the fp32 values
   int pair;                      // 1: CTA pairs (cta_group::2): 256 x bn tiles, each CTA of a 2-CTA cluster loads its 128 rows of A
                                  // and half of the B tile -- a third less L2 -> SM traffic per flop (bn >= 128 only; else ignored)
+  // optional per-row statistics of the final fp32 values (the prototype stage's reductions folded into the GEMM that produces
+  // the pooled features, so that those need not be written and read back): rowstat[(b*M + m) * 2*tiles_n + t][0..1] =
+  // (sum_n v^2, sum_n v * dotvec[(m % dot_mod) * dot_ld + n]) over the columns of column half-tile t
+  float* rowstat; const float* dotvec; long long dot_ld; int dot_mod;
 };
 
 int launch(const Gemm& g, cudaStream_t st);   // 0 or a negative pasn_status

@@ -32,7 +32,8 @@ struct Plan {
   int Pp;                      // column pitch of one plane of the token-major occurrence values
   int bn_c, tiles_n_c;         // tile width / count along S of the O GEMM (psum parts = 2 * tiles_n_c)
   int nb;                      // clips per chunk
-  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, total;
+  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, off_stat, off_vnorm, total;
+  int stat_parts;              // column half-tiles of the GEMM that produces features_extracted (row statistics per part)
 };
 
 inline int pick_bn(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
@@ -71,6 +72,9 @@ Plan make_plan(const pasn_dims& d) {
   p.off_pool = take(p.w2_first ? 0 : (size_t)p.nb * d.P * 2 * d.D * 2);
   p.off_f = take(p.w2_first ? (size_t)p.nb * S * ex * d.D * 2 : 0);
   p.off_fe = take((size_t)p.nb * d.P * d.D * 4);
+  p.stat_parts = 2 * ceil_div(d.D, d.D >= 256 ? 256 : 128);
+  p.off_stat = take((size_t)p.nb * d.P * p.stat_parts * 8);
+  p.off_vnorm = take((size_t)d.P * 4);
   p.total = o + 256;
   return p;
 }
@@ -297,6 +301,15 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   float* PSUM = reinterpret_cast<float*>(ws + p.off_psum);
   __nv_bfloat16* POOL = reinterpret_cast<__nv_bfloat16*>(ws + p.off_pool);
   float* FE = feats ? feats + (size_t)n0 * P * D : reinterpret_cast<float*>(ws + p.off_fe);
+  // Plain forward (nobody asked for features_extracted, no push): the GEMM that would write the pooled features leaves the
+  // two reductions the prototype stage needs (||f||^2, <f, v_p>) instead -- the features are neither stored nor read back.
+  static const int stats_env = [] { const char* e = getenv("PASN_TILED_STATS"); return e ? atoi(e) : 1; }();
+  // Worth it where the features are large against the L2 (config 5: 8 MB per clip); below that the round trip stays in L2
+  // and forward() keeps bit-identical logits with push_forward() (1: P >= 1024, 2: always, 0: never).
+  const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && P >= 1024)) && !occ_only && feats == nullptr && push == nullptr;
+  float* STAT = reinterpret_cast<float*>(ws + p.off_stat);
+  float* VNORM = reinterpret_cast<float*>(ws + p.off_vnorm);
+  if (fuse_stats && (rc = launch_proto_norms(w.prototypes, P, D, VNORM, st))) return rc;
   const __nv_bfloat16* W13 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w13);
   const __nv_bfloat16* W4 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w4);
   const __nv_bfloat16* W5 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w5);
@@ -425,6 +438,10 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       }
       g.act = tcg::ACT_NONE;
       g.out[0] = {FE, tcg::OUT_F32, (long long)D, (long long)P * D, 0};
+      if (fuse_stats) {
+        g.out[0].mode = tcg::OUT_NONE;
+        g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P;
+      }
       if ((rc = tcg::launch(g, st))) return rc;
     }
   } else {
@@ -456,10 +473,17 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.rowparts = PSUM; g.nparts = tok_c ? 1 : 2 * p.tiles_n_c; g.colvec = b2;
     g.act = tcg::ACT_NONE;
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};
+    if (fuse_stats) {
+      g.out[0].mode = tcg::OUT_NONE;
+      g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P;
+    }
     if ((rc = tcg::launch(g, st))) return rc;
   }
   }
   // ---- cosine / similarity / logits / distance / push keys (+ winner capture)
+  if (fuse_stats)
+    return launch_proto_from_stats(STAT, p.stat_parts, VNORM, w.last_layer, nb, P, d.K, logits + (size_t)n0 * d.K, sim + (size_t)n0 * P,
+                                   dist ? dist + (size_t)n0 * P : nullptr, st);
   pasn_push_args pa;
   const pasn_push_args* pp = nullptr;
   if (push) { pa = *push; pa.labels += n0; pa.global_offset += n0; pp = &pa; }

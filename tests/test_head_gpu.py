@@ -95,7 +95,9 @@ def test_cfg5_scaled_sweep_matches_oracle(dtype):
         assert_close(out["features_extracted"], rf.numpy(), FP32_RTOL, "features_extracted", atol_frac=fa)
         assert_close(out["occurrence_map"], ro.numpy(), FP32_RTOL, "occurrence_map", atol_frac=fa)
         assert_close(out["occ3"], ro.numpy(), FP32_RTOL, "compute_occurence_map", atol_frac=fa)
-    assert torch.equal(out["distance"], 1 - out["similarity"])
+    # forward() at P >= 1024 takes its cosine from row statistics left by the pooling GEMM (the 8 MB of pooled features per
+    # clip are never stored), push_forward() from the stored features: same fp32 formula, different summation order
+    assert float((out["distance"] - (1 - out["similarity"])).abs().max()) < 2e-6
 
 
 def test_cfg2_image_bf16_matches_oracle():

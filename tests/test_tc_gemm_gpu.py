@@ -34,7 +34,8 @@ class Gemm(C.Structure):     # pasn::tcg::Gemm
                 ("npass", C.c_int), ("a_off", C.c_int * 4), ("b_off", C.c_int * 4), ("bn", C.c_int),
                 ("bias", C.c_void_p), ("rowparts", C.c_void_p), ("nparts", C.c_int), ("colvec", C.c_void_p),
                 ("addin", Aux), ("signin", Aux), ("mask", Aux), ("act", C.c_int), ("out", Output * 2),
-                ("psum", C.c_void_p), ("psum_rounded", C.c_int), ("pair", C.c_int)]
+                ("psum", C.c_void_p), ("psum_rounded", C.c_int), ("pair", C.c_int),
+                ("rowstat", C.c_void_p), ("dotvec", C.c_void_p), ("dot_ld", C.c_longlong), ("dot_mod", C.c_int)]
 
 
 def _run(g):
@@ -199,3 +200,29 @@ def test_rank1_term_and_psum():
     ref = A.double() @ B.double().T + rp.double().sum(1, keepdim=True) * cv.double()
     _close(out, ref, 1e-5)
     _close(psum.sum(1), ref.sum(1), 1e-5)
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_row_statistics_without_an_output(pair):
+    """||row||^2 and <row, vector[row % mod]> of the fp32 result per column half-tile, with no output stored at all (the
+    prototype stage's reductions folded into the GEMM that makes the pooled features)."""
+    M, N, K, mod = 520, 512, 576, 40
+    A, B = _bf(_rand((M, K), 21)), _bf(_rand((N, K), 22))
+    bias = _rand((N,), 23)
+    V = _rand((mod, N), 24)
+    tiles_n = 2
+    stat = torch.full((M, 2 * tiles_n, 2), -1.0, device="cuda")
+    g = Gemm()
+    g.A, g.lda, g.ka = A.data_ptr(), K, K
+    g.B, g.ldb, g.kb = B.data_ptr(), K, K
+    g.M, g.N, g.K, g.batch, g.npass, g.bn, g.pair = M, N, K, 1, 1, 256, pair
+    g.bias = bias.data_ptr()
+    g.rowstat, g.dotvec, g.dot_ld, g.dot_mod = stat.data_ptr(), V.data_ptr(), N, mod
+    _run(g)
+    ref = A.double() @ B.double().T + bias.double()
+    Vr = V.double()[torch.arange(M, device="cuda") % mod]
+    _close(stat[:, :, 0].sum(1), (ref * ref).sum(1), 1e-5)
+    _close(stat[:, :, 1].sum(1), (ref * Vr).sum(1), 2e-5)
+    for t in range(2 * tiles_n):                      # each entry covers its own 128 columns
+        cols = slice(128 * t, 128 * t + 128)
+        _close(stat[:, t, 0], (ref[:, cols] ** 2).sum(1), 1e-5)
