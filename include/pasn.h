@@ -237,6 +237,9 @@ int pasn_debug_set_k1_variant(int variant);
  * by field), `desc_bytes` must equal pasn_debug_tc_gemm_desc_bytes(). */
 size_t pasn_debug_tc_gemm_desc_bytes(void);
 int pasn_debug_tc_gemm(const void* desc_host, size_t desc_bytes, void* stream);
+/* device buffer of 64 x 64 int64: globaltimer stamps of CTA 0 of the next (up to 64) GEMM launches of the tiled path, one row
+ * per launch (tools/trace_gemm.py; NULL = off) */
+int pasn_debug_set_gemm_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

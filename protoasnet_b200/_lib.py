@@ -26,7 +26,7 @@ SYMBOLS = [
     "pasn_debug_launch_count", "pasn_debug_time_main_kernel", "pasn_debug_last_main_kernel_ms",
     "pasn_debug_sm100_error", "pasn_debug_set_trace", "pasn_debug_set_k1_variant", "pasn_debug_fault", "pasn_debug_set_fault",
     "pasn_head_backward_workspace_bytes", "pasn_head_backward", "pasn_similarity_stats", "pasn_occurrence_lnorm",
-    "pasn_debug_tc_gemm_desc_bytes", "pasn_debug_tc_gemm",
+    "pasn_debug_tc_gemm_desc_bytes", "pasn_debug_tc_gemm", "pasn_debug_set_gemm_trace",
 ]
 
 
@@ -121,6 +121,8 @@ def load() -> C.CDLL:
     lib.pasn_debug_tc_gemm_desc_bytes.restype = sz
     lib.pasn_debug_tc_gemm.restype = C.c_int
     lib.pasn_debug_tc_gemm.argtypes = [vp, sz, vp]
+    lib.pasn_debug_set_gemm_trace.restype = C.c_int
+    lib.pasn_debug_set_gemm_trace.argtypes = [vp]
     if lib.pasn_abi_version() != 2:
         raise PasnError("libpasn_b200.so ABI version mismatch")
     _lib = lib

@@ -140,6 +140,8 @@ extern "C" int pasn_debug_tc_gemm(const void* desc_host, size_t desc_bytes, void
   return tcg::launch(*reinterpret_cast<const tcg::Gemm*>(desc_host), reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int pasn_debug_set_gemm_trace(void* device_buffer) { tcg::set_trace(device_buffer); return PASN_OK; }
+
 extern "C" int pasn_abi_version(void) { return PASN_ABI_VERSION; }
 
 extern "C" const char* pasn_strerror(int status) {

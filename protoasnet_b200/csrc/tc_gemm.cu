@@ -48,7 +48,7 @@ constexpr uint32_t SM_VEC = SM_STG + EPI_WARPS * 2 * SLAB_BYTES;  // 212992: per
 constexpr uint32_t SM_BAR = SM_VEC + EPI_WARPS * 1024;            // 221184
 constexpr uint32_t SM_MISC = SM_BAR + 24 * 8;
 constexpr uint32_t SMEM_BYTES = SM_MISC + 64;
-enum { B_FULL = 0, B_EMPTY = MAX_STAGES, B_ACCFULL = 2 * MAX_STAGES, B_ACCEMPTY = 2 * MAX_STAGES + 2 };
+enum { B_FULL = 0, B_EMPTY = MAX_STAGES, B_ACCFULL = 2 * MAX_STAGES, B_ACCEMPTY = 2 * MAX_STAGES + 2, B_WARM = 2 * MAX_STAGES + 4 };
 
 struct alignas(64) KParams {
   CUtensorMap tmA, tmB, tmO[4];   // out0 (hi), out0 lo, out1 (hi), out1 lo
@@ -56,7 +56,9 @@ struct alignas(64) KParams {
   int out_tma[2];
   int tall;   // 1: a tile has two 128-row (per CTA) sub-tiles that share each B stage; they take the two accumulator buffers
   int tiles_m, tiles_n, nkb;
+  int warm;   // 1: the producer touches its first operand boxes before waiting for the grid in front (see the kernel)
   int* err;
+  long long* trace;   // optional: 64 globaltimer stamps of CTA 0 (tools/trace_gemm.py)
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -103,6 +105,13 @@ static __device__ __noinline__ bool wait_slow(uint64_t* bar, uint32_t parity, in
   }
   return true;
 }
+__device__ __forceinline__ long long gtimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TCG_TRACE(slot) do { if (kp.trace != nullptr && blockIdx.x == 0) kp.trace[slot] = gtimer_ns(); } while (0)
+#define TCG_TRACE1(slot) do { if (kp.trace != nullptr && blockIdx.x == 1) kp.trace[slot] = gtimer_ns(); } while (0)
 __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return true;
   return wait_slow(bar, parity, err, code);
@@ -123,12 +132,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (tid == 0) *reinterpret_cast<volatile int*>(kp.err) = 700;
     return;
   }
+  if (tid == 0) TCG_TRACE(0);
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;         // rank in the cluster
   const uint32_t rank = crank & 1u;                             // rank in the pair: 0 = leader
   const uint32_t pq = crank >> 1;                               // pair inside a quad
   if (tid == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], QUAD ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_ACCFULL + i], 1); mbar_init(&bars[B_ACCEMPTY + i], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
+    mbar_init(&bars[B_WARM], 1);
     fence_mbar_init();
     prefetch_tmap(&kp.tmA);
     prefetch_tmap(&kp.tmB);
@@ -141,8 +152,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
   // programmatic dependent launch: the chain's GEMMs follow each other on one stream; the next launch may set itself up
   // (barriers, TMEM, tensor-map prefetch) while this grid drains, and nothing here touches global memory before the
   // grid in front of it has completed
+  if (tid == 0) TCG_TRACE(1);   // set-up done
   griddep_launch_dependents();
-  griddep_wait();
+  // (the producer thread waits below, after warming up its first loads; epilogue warps that may read the statistics' vectors
+  // early do so first)
+  const bool stat_early = g.rowstat != nullptr && g.dot_early != 0;
+  if (warp != 0 && !(stat_early && warp >= EPI_WARP0)) griddep_wait();
   const uint32_t tbase = *tmem_ptr_s;
   const uint32_t sbase = smem_u32(smem);
   const int bn = g.bn;
@@ -172,6 +187,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         if constexpr (PAIR) tma_load_3d_2sm(dst, map, c0, c1, c2, bar);
         else tma_load_3d(dst, map, c0, c1, c2, bar);
       };
+      if (kp.warm && tile0 < ntiles) {
+        // The first load of a launch takes ~2.7 us (tensor-map fetch, translation, cold lines) against ~1 us later on: touch
+        // the first boxes of both operands while the grid in front is still draining.  What lands may be stale (A is being
+        // written by that grid) and is thrown away; the real loads below overwrite the stage.
+        const int b = tile0 / tiles_per_batch, r = tile0 - b * tiles_per_batch;
+        const int m0 = (r / kp.tiles_n) * BMT + (int)pq * BMP + (int)rank * BM, n0 = (r % kp.tiles_n) * bn + (int)rank * bnl;
+        const bool split_k = g.k_rows_per_batch > 0;
+        const int krow = split_k ? b * g.k_rows_per_batch : 0;
+        const uint32_t a_tx = g.a_mn_major ? 8192u : A_BYTES, b_tx = g.b_mn_major ? 8192u : (uint32_t)bnl * 128u;
+        mbar_arrive_expect_tx(&bars[B_WARM], a_tx + b_tx);
+        if (!g.a_mn_major) tma_load_3d(sbase, &kp.tmA, g.a_off[0], m0, g.a_batched ? b : 0, &bars[B_WARM]);
+        else tma_load_3d(sbase, &kp.tmA, g.a_off[0] + m0, krow, (g.a_batched && !split_k) ? b : 0, &bars[B_WARM]);
+        if (!g.b_mn_major) tma_load_3d(sbase + A_BYTES, &kp.tmB, g.b_off[0], n0, g.b_batched ? b : 0, &bars[B_WARM]);
+        else tma_load_3d(sbase + A_BYTES, &kp.tmB, g.b_off[0] + n0, krow, (g.b_batched && !split_k) ? b : 0, &bars[B_WARM]);
+      }
+      griddep_wait();
+      TCG_TRACE(2);   // the grid in front has completed
+      if (kp.warm && tile0 < ntiles) ok = bwait(&bars[B_WARM], 0, kp.err, 702);
       for (int t = tile0; t < ntiles && ok; t += tstep) {
         const int b = t / tiles_per_batch, r = t - b * tiles_per_batch;
         const int m0 = (r / kp.tiles_n) * BMT + (int)pq * BMP + (int)rank * BM, n0 = (r % kp.tiles_n) * bn + (int)rank * bnl;
@@ -181,6 +214,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_EMPTY + s], ph ^ 1, kp.err, 701))) break;
             const uint32_t dst = sbase + s * stage_bytes;
+            if (t == tile0 && pass == 0 && kb == 0) TCG_TRACE(6);   // first load goes out
             if (rank == 0) mbar_arrive_expect_tx(&bars[B_FULL + s], stage_tx);
             const int krow = krow0 + kb * BK;   // K coordinate of MN-major operands (rows)
             for (int u = 0; u < nu; ++u) {
@@ -250,6 +284,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         for (int pass = 0; pass < g.npass && ok; ++pass) {
           for (int kb = 0; kb < kp.nkb; ++kb) {
             if (!(ok = bwait(&bars[B_FULL + s], ph, kp.err, 712))) break;
+            if (i == 0 && pass == 0 && kb == 0) TCG_TRACE(3);   // first operand stage has landed
+            if (pass == 0 && kb == 0 && i < 16) TCG_TRACE(48 + i);   // ... and each tile's first one
             tc_fence_after();
             const uint32_t sa = sbase + s * stage_bytes;
             const uint32_t alo = desc_lo(sa, a_lbo), blo = desc_lo(sa + a_stage, b_lbo);
@@ -267,6 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           }
         }
         if (ok) {
+          if (i == 0) TCG_TRACE(4);   // first tile's MMAs issued
           commit(bar0 + 8u * (B_ACCFULL + buf));
           if (nu == 2) commit(bar0 + 8u * (B_ACCFULL + 1));
         }
@@ -291,6 +328,34 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const int half_cols = bn / nh;
     const int ngroups = half_cols / 64;
     uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
+    // row statistics with the vectors' slices cached in the staging slabs (see below)
+    const bool stat_cached = !PAIR && g.rowstat != nullptr && !kp.out_tma[0] && !kp.out_tma[1] && g.M <= 64 && kp.tiles_m == 1 &&
+                             nh == 2 && (g.N & 63) == 0 && (g.dot_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dotvec) & 15) == 0;
+    int stat_key0 = -1, stat_key1 = -1;
+    // slice of the vectors for this warp's rows and one column group -> slab(s); the row pairs are walked from a different
+    // start in every CTA and warp: all CTAs read the same few KB, in step they queue up on the same L2 lines (19 us measured)
+    auto stat_fill = [&](int cg, int col0) {
+      float* stg = reinterpret_cast<float*>(smem + SM_STG + (uint32_t)(w + 2 * cg) * 2u * SLAB_BYTES);
+      const int rot = (int)((blockIdx.x * 5u + (uint32_t)w * 3u + (uint32_t)cg * 7u) & 15u);
+      __syncwarp();
+#pragma unroll 8
+      for (int it0 = 0; it0 < 16; ++it0) {
+        const int it = (it0 + rot) & 15;
+        const int r = 2 * it + (lane >> 4), j = lane & 15;
+        const int rr = q * 32 + r;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < g.M) w4 = __ldg(reinterpret_cast<const float4*>(g.dotvec + (long long)(rr % g.dot_mod) * g.dot_ld + col0) + j);
+        *reinterpret_cast<float4*>(stg + r * 64 + ((j ^ (r & 7)) << 2)) = w4;
+      }
+      __syncwarp();
+    };
+    if (stat_cached && q < 2 && tile0 < ntiles) {   // the first tile's slices, while its operands are still on their way
+      const int n00 = ((tile0 % tiles_per_batch) % kp.tiles_n) * bn + hw * half_cols;
+      stat_fill(0, n00);
+      stat_key0 = n00;
+      if (ngroups > 1) { stat_fill(1, n00 + 64); stat_key1 = n00 + 64; }
+    }
+    if (stat_early) griddep_wait();
     bool ok = true;
     int i = 0;
     // one 64-column group of one output leaves through the staging slab(s) + TMA store(s)
@@ -427,6 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         __syncwarp();
       }
       if (!(ok = bwait(&bars[B_ACCFULL + buf], (i >> 1) & 1, kp.err, 721))) break;
+      if (w == 0 && lane == 0) { if (tv == 0) TCG_TRACE(5); TCG_TRACE(7); if (tv < 16) TCG_TRACE(16 + tv); }   // first / last / each accumulator handed over
       tc_fence_after();
       if (h >= nh || m0 + q * 32 >= g.M) {
         // nothing to read for this warp (unused column half, or all 32 rows past M: the per-clip GEMMs with M = P = 40 only
@@ -521,7 +587,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if (mk) apply_bf16(mk, mcs, false);
           }
         }
-        if (g.rowstat != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
+        if (stat_cached) {
+          // Few rows per batch item (the per-clip pooling GEMMs with M = P <= 64): every tile of this CTA pairs the same rows
+          // with the same vectors, and the warps of the two upper row groups are idle -- their staging slabs hold this
+          // warp's second column group.  The 32 x 64 slices are read once per CTA (whole 256-byte rows, chunks swizzled by
+          // the row: conflict-free on both sides) instead of once per tile by every SM from the same few L2 lines.
+          float* stg = reinterpret_cast<float*>(smem + SM_STG + (uint32_t)(w + 2 * cg) * 2u * SLAB_BYTES);
+          if ((cg ? stat_key1 : stat_key0) != col0) {
+            stat_fill(cg, col0);
+            if (cg) stat_key1 = col0; else stat_key0 = col0;
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(stg + lane * 64 + ((j4 ^ (lane & 7)) << 2));
+            st_ff = fmaf(v[4 * j4], v[4 * j4], st_ff);         st_dot = fmaf(v[4 * j4], w4.x, st_dot);
+            st_ff = fmaf(v[4 * j4 + 1], v[4 * j4 + 1], st_ff); st_dot = fmaf(v[4 * j4 + 1], w4.y, st_dot);
+            st_ff = fmaf(v[4 * j4 + 2], v[4 * j4 + 2], st_ff); st_dot = fmaf(v[4 * j4 + 2], w4.z, st_dot);
+            st_ff = fmaf(v[4 * j4 + 3], v[4 * j4 + 3], st_ff); st_dot = fmaf(v[4 * j4 + 3], w4.w, st_dot);
+          }
+        } else if (g.rowstat != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
           const float* vr = g.dotvec + (long long)(row % g.dot_mod) * g.dot_ld + col0;
           if (col0 + 64 <= g.N && ((reinterpret_cast<uintptr_t>(vr) & 15) == 0)) {
 #pragma unroll
@@ -565,18 +649,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
           else store_direct(o, v, col0, row, b, row_ok);
         }
       }
+      if (w == 0 && lane == 0 && tv < 16) TCG_TRACE(32 + tv);   // this tile's rows are out of the registers
       if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
       if (g.rowstat != nullptr && row_ok)
         *reinterpret_cast<float2*>(g.rowstat + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) =
             (split_out && hw == 1) ? make_float2(0.f, 0.f) : make_float2(st_ff, st_dot);
     }
+    if (w == 0 && lane == 0) { TCG_TRACE(8); TCG_TRACE1(13); }   // last tile's rows are out of the registers
+    if (w == 4 && lane == 0) TCG_TRACE(12);
     if (lane == 0) bulk_wait<0>();   // outstanding TMA stores must complete before the CTA's smem goes away
     __syncwarp();
+    if (w == 0 && lane == 0) { TCG_TRACE(9); TCG_TRACE1(14); }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TCG_TRACE(11);
   if constexpr (PAIR) cluster_sync_all();   // the partner may still read this CTA's shared memory / signal its barriers
   if (warp == 2) { if constexpr (PAIR) tmem_dealloc2(tbase, 512); else tmem_dealloc(tbase, 512); }
+  if (tid == 0) TCG_TRACE(10);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -621,6 +711,11 @@ bool out_aligned(const Output& o) {
 
 bool available() { return encode_fn() != nullptr; }
 
+static long long* g_trace = nullptr;
+static int g_trace_slot = 0;
+void set_trace(void* dev_buf) { g_trace = reinterpret_cast<long long*>(dev_buf); g_trace_slot = 0; }
+
+
 
 int launch(const Gemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return PASN_OK;
@@ -636,7 +731,8 @@ int launch(const Gemm& g, cudaStream_t st) {
   static const int pair_env = [] { const char* e = getenv("PASN_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // A/B switch
   // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py); short-K GEMMs are bound by
   // their epilogues and lose a little to the cross-CTA hand-offs
-  const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= 8)) && g.bn >= 128 && g.M > BM;
+  static const int pair_min = [] { const char* e = getenv("PASN_GEMM_PAIR_MIN"); return e ? atoi(e) : 8; }();
+  const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= pair_min)) && g.bn >= 128 && g.M > BM;
   // two pairs per cluster sharing the B tile by multicast (full-width tiles, at least two pair tiles along M).  Correct (unit
   // tests with PASN_GEMM_PAIR=1 PASN_GEMM_QUAD=1) but measured SLOWER than plain pairs -- 8192^3: 694 vs 1264 TFLOP/s, layer-1
   // shape 602 vs 1005: the stage hand-back needs both pairs' commits and the 4-deep ring cannot cover the extra cluster
@@ -654,7 +750,12 @@ int launch(const Gemm& g, cudaStream_t st) {
   KParams kp;
   kp.g = g;
   kp.err = fault;
+  kp.trace = nullptr;
+  if (g_trace != nullptr && g_trace_slot < 64) kp.trace = g_trace + 64 * g_trace_slot++;   // debug: a row of stamps per launch
   kp.tall = tall ? 1 : 0;
+  static const int warm_env = [] { const char* e = getenv("PASN_GEMM_WARM"); return e ? atoi(e) : 0; }();
+  kp.warm = (warm_env != 0 && !quad) ? 1 : 0;
+
   kp.tiles_m = ceil_div(g.M, cl * BM * (tall ? 2 : 1));
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);

@@ -62,8 +62,10 @@ struct Gemm {
   // the pooled features, so that those need not be written and read back): rowstat[(b*M + m) * 2*tiles_n + t][0..1] =
   // (sum_n v^2, sum_n v * dotvec[(m % dot_mod) * dot_ld + n]) over the columns of column half-tile t
   float* rowstat; const float* dotvec; long long dot_ld; int dot_mod;
+  int dot_early;                 // dotvec is not written by the kernel in front on the stream: it may be read before that one has completed
 };
 
+void set_trace(void* dev_buf);   // debug: 64 rows of 64 int64 globaltimer stamps of CTA 0, one row per launch (null = off)
 int launch(const Gemm& g, cudaStream_t st);   // 0 or a negative pasn_status
 bool available();                             // driver entry point for tensor-map encoding found
 

@@ -304,9 +304,11 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   // Plain forward (nobody asked for features_extracted, no push): the GEMM that would write the pooled features leaves the
   // two reductions the prototype stage needs (||f||^2, <f, v_p>) instead -- the features are neither stored nor read back.
   static const int stats_env = [] { const char* e = getenv("PASN_TILED_STATS"); return e ? atoi(e) : 1; }();
-  // Worth it where the features are large against the L2 (config 5: 8 MB per clip); below that the round trip stays in L2
-  // and forward() keeps bit-identical logits with push_forward() (1: P >= 1024, 2: always, 0: never).
-  const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && P >= 1024)) && !occ_only && feats == nullptr && push == nullptr;
+  // Used where it pays (1, default): many prototypes (config 5: 8 MB of features per clip), and the per-clip pooling GEMM of
+  // few prototypes straight into features (image head: the GEMM keeps the prototype slices in shared memory).  Elsewhere the
+  // statistics' vector reads (a row per lane) cost the epilogue more than the round trip.  2: always, 0: never.
+  const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && (P >= 1024 || (P <= 64 && p.w2_first)))) && !occ_only &&
+                          feats == nullptr && push == nullptr;
   float* STAT = reinterpret_cast<float*>(ws + p.off_stat);
   float* VNORM = reinterpret_cast<float*>(ws + p.off_vnorm);
   if (fuse_stats && (rc = launch_proto_norms(w.prototypes, P, D, VNORM, st))) return rc;
@@ -440,7 +442,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       g.out[0] = {FE, tcg::OUT_F32, (long long)D, (long long)P * D, 0};
       if (fuse_stats) {
         g.out[0].mode = tcg::OUT_NONE;
-        g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P;
+        g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P; g.dot_early = 1;   // (parameters: the chain does not write them)
       }
       if ((rc = tcg::launch(g, st))) return rc;
     }
@@ -475,7 +477,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
     g.out[0] = {FE, tcg::OUT_F32, (long long)D, 0, 0};
     if (fuse_stats) {
       g.out[0].mode = tcg::OUT_NONE;
-      g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P;
+      g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P; g.dot_early = 1;   // (parameters: the chain does not write them)
     }
     if ((rc = tcg::launch(g, st))) return rc;
   }

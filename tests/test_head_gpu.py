@@ -279,8 +279,10 @@ def test_tiled_path_shape_sweep(shape, layout, dtype):
     tol = BF16_RTOL if bf else FP32_RTOL
     assert_close(out["similarity"], (1 - rd).numpy(), tol, "similarity")
     assert_close(out["logits"], rl.numpy(), tol, "logits")
-    assert torch.equal(out["distance"], 1 - out["similarity"])
-    assert torch.equal(out["logits"], out["logits2"])
+    # forward() may take its cosine from row statistics folded into the pooling GEMM (few prototypes, W2 before the pooling),
+    # push_forward() from the stored features: the same fp32 formula in another summation order
+    assert float((out["distance"] - (1 - out["similarity"])).abs().max()) < 2e-6
+    assert_close(out["logits"], out["logits2"].cpu().numpy(), 1e-5, "forward vs push_forward logits", atol_frac=2e-6)
     if bf:
         # bf16 hidden activations (2^-9 relative each) are averaged over the S voxels of a clip: the fewer voxels, the
         # more of that rounding is left in the pooled features (north_star's 1e-3 bound is on similarities / logits, above)

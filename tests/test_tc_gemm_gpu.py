@@ -35,7 +35,8 @@ class Gemm(C.Structure):     # pasn::tcg::Gemm
                 ("bias", C.c_void_p), ("rowparts", C.c_void_p), ("nparts", C.c_int), ("colvec", C.c_void_p),
                 ("addin", Aux), ("signin", Aux), ("mask", Aux), ("act", C.c_int), ("out", Output * 2),
                 ("psum", C.c_void_p), ("psum_rounded", C.c_int), ("pair", C.c_int),
-                ("rowstat", C.c_void_p), ("dotvec", C.c_void_p), ("dot_ld", C.c_longlong), ("dot_mod", C.c_int)]
+                ("rowstat", C.c_void_p), ("dotvec", C.c_void_p), ("dot_ld", C.c_longlong), ("dot_mod", C.c_int),
+                ("dot_early", C.c_int)]
 
 
 def _run(g):
@@ -226,3 +227,28 @@ def test_row_statistics_without_an_output(pair):
     for t in range(2 * tiles_n):                      # each entry covers its own 128 columns
         cols = slice(128 * t, 128 * t + 128)
         _close(stat[:, t, 0], (ref[:, cols] ** 2).sum(1), 1e-5)
+
+
+@pytest.mark.parametrize("bn", [256, 128])
+def test_row_statistics_few_rows_per_batch_item(bn):
+    """The per-clip pooling shape (M = P = 40 rows per batch item, several tiles per CTA): the vectors' slices are read into
+    shared memory once per CTA and reused by every tile with the same columns."""
+    M, N, K, batch, mod = 40, 512, 64, 300, 40
+    A, B = _bf(_rand((batch, M, K), 31)), _bf(_rand((batch, N, K), 32))
+    V = _rand((mod, N), 33)
+    tiles_n = N // bn
+    stat = torch.full((batch, M, 2 * tiles_n, 2), -1.0, device="cuda")
+    g = Gemm()
+    g.A, g.lda, g.a_bs, g.a_batched, g.ka = A.data_ptr(), K, M * K, 1, K
+    g.B, g.ldb, g.b_bs, g.b_batched, g.kb = B.data_ptr(), K, N * K, 1, K
+    g.M, g.N, g.K, g.batch, g.npass, g.bn = M, N, K, batch, 1, bn
+    g.rowstat, g.dotvec, g.dot_ld, g.dot_mod = stat.data_ptr(), V.data_ptr(), N, mod
+    g.dot_early = 1 if bn == 128 else 0     # the vectors may be read before the kernel in front has completed
+    _run(g)
+    ref = torch.bmm(A.double(), B.double().transpose(1, 2))
+    _close(stat[..., 0].sum(2), (ref * ref).sum(2), 1e-5)
+    _close(stat[..., 1].sum(2), (ref * V.double()[None]).sum(2), 2e-5)
+    half = bn // 2
+    for t in range(2 * tiles_n):                      # each entry covers its own column half-tile
+        cols = slice(half * t, half * t + half)
+        _close(stat[:, :, t, 1], (ref[:, :, cols] * V.double()[None, :, cols]).sum(2), 2e-5)
