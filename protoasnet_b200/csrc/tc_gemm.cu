@@ -120,9 +120,18 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, 
 
 }  // namespace
 
-template <int MODE>   // 0: one CTA per tile, 1: CTA pairs, 2: two pairs per cluster sharing the B tile by multicast
+// EPI selects how much of the epilogue is compiled in.  The generic epilogue (EPI_FULL) is ~10 k instructions of unrolled
+// 64-element loops behind launch-uniform branches; a tile's path through it jumps from one cold instruction-cache line to the
+// next (ncu: 20-30 % of the short GEMMs' issue slots lost to stall_no_inst).  The two shapes that carry the forward chain get
+// their own lean instantiations: EPI_LEAN = bias / rank-1 term / activation and TMA-stored outputs only, EPI_STAT = no output
+// at all, row statistics only.
+enum { EPI_FULL = 0, EPI_LEAN = 1, EPI_STAT = 2, EPI_DIRECT = 3 };   // EPI_DIRECT = EPI_LEAN + plain stores / two outputs split between the warp groups
+template <int MODE, int EPI>   // MODE 0: one CTA per tile, 1: CTA pairs, 2: two pairs per cluster sharing the B tile by multicast
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ KParams kp) {
   constexpr bool PAIR = MODE >= 1, QUAD = MODE == 2;
+  constexpr bool E_AUX = EPI == EPI_FULL, E_PSUM = EPI == EPI_FULL, E_STAT = EPI == EPI_FULL || EPI == EPI_STAT,
+                 E_DIRECT = EPI == EPI_FULL || EPI == EPI_DIRECT, E_OUT = EPI != EPI_STAT, E_ABSOUT = EPI == EPI_FULL,
+                 E_SPLIT = EPI == EPI_FULL || EPI == EPI_DIRECT;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
@@ -319,17 +328,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     // instruction per accumulator element costs ~1/4 cycle per element of the tile), so everything that is uniform
     // over the launch is decided by branches around the element loops, never by selects inside them.
     const bool has_vec = g.bias != nullptr || (g.rowparts != nullptr && g.colvec != nullptr);
-    const bool has_aux = g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr;
+    const bool has_aux = E_AUX && (g.addin.ptr != nullptr || g.signin.ptr != nullptr || g.mask.ptr != nullptr);
+    float* const psum_p = E_PSUM ? g.psum : nullptr;
+    float* const rowstat_p = E_STAT ? g.rowstat : nullptr;
     const int nh = bn >= 128 ? 2 : 1;            // column halves in use (a 64-wide tile is one 64-column group: half 0 only)
     // a 64-wide tile with two outputs: the second warp group, otherwise idle, reads the same columns and takes output 1
     // (the channel-major plain stores of the occurrence map run next to the TMA store of the token-major copy)
-    const bool split_out = nh == 1 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE;
+    const bool split_out = E_SPLIT && nh == 1 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE;
     const int h = split_out ? 0 : hw;            // column half this warp reads
     const int half_cols = bn / nh;
     const int ngroups = half_cols / 64;
     uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
     // row statistics with the vectors' slices cached in the staging slabs (see below)
-    const bool stat_cached = !PAIR && g.rowstat != nullptr && !kp.out_tma[0] && !kp.out_tma[1] && g.M <= 64 && kp.tiles_m == 1 &&
+    const bool stat_cached = !PAIR && rowstat_p != nullptr && !kp.out_tma[0] && !kp.out_tma[1] && g.M <= 64 && kp.tiles_m == 1 &&
                              nh == 2 && (g.N & 63) == 0 && (g.dot_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dotvec) & 15) == 0;
     int stat_key0 = -1, stat_key1 = -1;
     // slice of the vectors for this warp's rows and one column group -> slab(s); the row pairs are walked from a different
@@ -499,9 +510,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         // need two of the four row groups): release the accumulator, keep the psum table dense
         __syncwarp();
         if (lane == 0) acc_release(buf);
-        if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = 0.f;
-        if (g.rowstat != nullptr && row_ok)
-          *reinterpret_cast<float2*>(g.rowstat + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) = make_float2(0.f, 0.f);
+        if (psum_p != nullptr && row_ok) psum_p[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = 0.f;
+        if (rowstat_p != nullptr && row_ok)
+          *reinterpret_cast<float2*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) = make_float2(0.f, 0.f);
         continue;
       }
       for (int cg = 0; cg < ngroups; ++cg) {
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             st_ff = fmaf(v[4 * j4 + 2], v[4 * j4 + 2], st_ff); st_dot = fmaf(v[4 * j4 + 2], w4.z, st_dot);
             st_ff = fmaf(v[4 * j4 + 3], v[4 * j4 + 3], st_ff); st_dot = fmaf(v[4 * j4 + 3], w4.w, st_dot);
           }
-        } else if (g.rowstat != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
+        } else if (rowstat_p != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
           const float* vr = g.dotvec + (long long)(row % g.dot_mod) * g.dot_ld + col0;
           if (col0 + 64 <= g.N && ((reinterpret_cast<uintptr_t>(vr) & 15) == 0)) {
 #pragma unroll
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
               if (col0 + j < g.N) { st_ff = fmaf(v[j], v[j], st_ff); st_dot = fmaf(v[j], __ldg(vr + j), st_dot); }
           }
         }
-        if (g.psum != nullptr) {
+        if (psum_p != nullptr) {
           if (col0 + 64 <= g.N) {
             if (g.psum_rounded) {
 #pragma unroll
@@ -640,19 +651,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           const Output& o = g.out[mi];
-          if (o.mode == OUT_NONE || (split_out && mi != hw)) continue;
-          if (o.absval) {   // |value| next to an output that keeps the sign: only the first output may be the signed one
+          if (!E_OUT || o.mode == OUT_NONE || (split_out && mi != hw)) continue;
+          if (E_ABSOUT && o.absval) {   // |value| next to an output that keeps the sign: only the first output may be the signed one
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = fabsf(v[j]);
           }
-          if (kp.out_tma[mi]) store_tma(o, mi, v, col0, m0 + q * 32, b);
+          if (!E_DIRECT || kp.out_tma[mi]) store_tma(o, mi, v, col0, m0 + q * 32, b);
           else store_direct(o, v, col0, row, b, row_ok);
         }
       }
       if (w == 0 && lane == 0 && tv < 16) TCG_TRACE(32 + tv);   // this tile's rows are out of the registers
-      if (g.psum != nullptr && row_ok) g.psum[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
-      if (g.rowstat != nullptr && row_ok)
-        *reinterpret_cast<float2*>(g.rowstat + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) =
+      if (psum_p != nullptr && row_ok) psum_p[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
+      if (rowstat_p != nullptr && row_ok)
+        *reinterpret_cast<float2*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) =
             (split_out && hw == 1) ? make_float2(0.f, 0.f) : make_float2(st_ff, st_dot);
     }
     if (w == 0 && lane == 0) { TCG_TRACE(8); TCG_TRACE1(13); }   // last tile's rows are out of the registers
@@ -722,16 +733,20 @@ int launch(const Gemm& g, cudaStream_t st) {
   if (g.npass < 1 || g.npass > 4 || (g.bn != 64 && g.bn != 128 && g.bn != 256)) return PASN_ERR_INVALID;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
-      return PASN_ERR_CUDA;
+    const void* fns[] = {(const void*)tc_gemm_kernel<0, EPI_FULL>, (const void*)tc_gemm_kernel<1, EPI_FULL>, (const void*)tc_gemm_kernel<2, EPI_FULL>,
+                         (const void*)tc_gemm_kernel<0, EPI_LEAN>, (const void*)tc_gemm_kernel<1, EPI_LEAN>,
+                         (const void*)tc_gemm_kernel<0, EPI_STAT>, (const void*)tc_gemm_kernel<1, EPI_STAT>,
+                         (const void*)tc_gemm_kernel<0, EPI_DIRECT>, (const void*)tc_gemm_kernel<1, EPI_DIRECT>};
+    for (const void* f : fns)
+      if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return PASN_ERR_CUDA;
     attr_done = true;
   }
   static const int pair_env = [] { const char* e = getenv("PASN_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // A/B switch
   // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py); short-K GEMMs are bound by
-  // their epilogues and lose a little to the cross-CTA hand-offs
-  static const int pair_min = [] { const char* e = getenv("PASN_GEMM_PAIR_MIN"); return e ? atoi(e) : 8; }();
+  // their epilogues and lose to the cross-CTA hand-offs: the launch trace (tools/trace_gemm.py) shows the partner CTA's
+  // last rows leaving 1.5-1.9 us after the leader's and the closing cluster barrier waiting for them -- ~3 us per launch,
+  // and the K = 512 GEMMs of the chain ran 4 us faster (of 64) on single CTAs.  Hence from 16 k-block passes per tile.
+  static const int pair_min = [] { const char* e = getenv("PASN_GEMM_PAIR_MIN"); return e ? atoi(e) : 16; }();
   const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= pair_min)) && g.bn >= 128 && g.M > BM;
   // two pairs per cluster sharing the B tile by multicast (full-width tiles, at least two pair tiles along M).  Correct (unit
   // tests with PASN_GEMM_PAIR=1 PASN_GEMM_QUAD=1) but measured SLOWER than plain pairs -- 8192^3: 694 vs 1264 TFLOP/s, layer-1
@@ -753,7 +768,7 @@ int launch(const Gemm& g, cudaStream_t st) {
   kp.trace = nullptr;
   if (g_trace != nullptr && g_trace_slot < 64) kp.trace = g_trace + 64 * g_trace_slot++;   // debug: a row of stamps per launch
   kp.tall = tall ? 1 : 0;
-  static const int warm_env = [] { const char* e = getenv("PASN_GEMM_WARM"); return e ? atoi(e) : 0; }();
+  static const int warm_env = [] { const char* e = getenv("PASN_GEMM_WARM"); return e ? atoi(e) : 1; }();
   kp.warm = (warm_env != 0 && !quad) ? 1 : 0;
 
   kp.tiles_m = ceil_div(g.M, cl * BM * (tall ? 2 : 1));
@@ -822,8 +837,28 @@ int launch(const Gemm& g, cudaStream_t st) {
       ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    const cudaError_t e = quad ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2>, kp)
-                               : (pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0>, kp));
+    // the leanest epilogue that can do what this launch asks for
+    static const int epi_env = [] { const char* e = getenv("PASN_GEMM_EPI"); return e ? atoi(e) : 1; }();   // 0: always the generic one
+    bool any_out = false, all_tma = true, plain = true;
+    for (int mi = 0; mi < 2; ++mi) {
+      if (g.out[mi].mode == OUT_NONE) continue;
+      any_out = true;
+      if (!kp.out_tma[mi]) all_tma = false;
+      if (g.out[mi].absval) plain = false;
+    }
+    if (g.addin.ptr || g.signin.ptr || g.mask.ptr || g.psum) plain = false;
+    if (g.bn == 64 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE) all_tma = false;   // two outputs split between the warp groups
+    int epi = EPI_FULL;
+    if (epi_env && !quad && plain) {
+      if (g.rowstat == nullptr) epi = all_tma ? EPI_LEAN : EPI_DIRECT;
+      else if (!any_out) epi = EPI_STAT;
+    }
+    cudaError_t e;
+    if (quad) e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2, EPI_FULL>, kp);
+    else if (epi == EPI_LEAN) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_LEAN>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_LEAN>, kp);
+    else if (epi == EPI_DIRECT) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_DIRECT>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_DIRECT>, kp);
+    else if (epi == EPI_STAT) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_STAT>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_STAT>, kp);
+    else e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_FULL>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_FULL>, kp);
     if (e != cudaSuccess) return PASN_ERR_CUDA;
   }
   PASN_LAUNCH_CHECK();
