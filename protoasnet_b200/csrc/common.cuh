@@ -103,10 +103,10 @@ int launch_proto_stage(const float* feats /*[N,P,D]*/, const float* protos, cons
                        int D, int K, float* logits, float* sim, float* dist, const pasn_push_args* push,
                        cudaStream_t st);
 
-// prototype stage from per-row statistics left by the GEMM that made the pooled features (tiled path, plain forward)
-int launch_proto_norms(const float* protos, int P, int D, float* vnorm, cudaStream_t st);
-int launch_proto_from_stats(const float* stat, int nparts, const float* vnorm, const float* last_layer, int N, int P, int K,
-                            float* logits, float* sim, float* dist, cudaStream_t st);
+// prototype stage from per-row statistics left by the GEMM that made the pooled features (tiled path, plain forward):
+// stat[(n*P + p) * nparts + t] = (||f||^2, <f, v_p>, ||v_p||^2, -) over the columns of part t
+int launch_proto_from_stats(const float* stat, int nparts, const float* last_layer, int N, int P, int K, float* logits, float* sim,
+                            float* dist, cudaStream_t st);
 
 // ---- tiled tcgen05 path (tiled.cu, tc_gemm.cu): chain of TMA-fed GEMMs, bf16 or fp32 (hi/lo split) -----------------
 bool tiled_supported(const pasn_dims& d);

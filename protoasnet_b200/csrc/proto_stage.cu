@@ -169,32 +169,53 @@ __global__ void __launch_bounds__(PS_THREADS) proto_logits_wide_kernel(const flo
   }
 }
 
-// Prototype stage from per-row statistics (the GEMM that produced the pooled features left ||f||^2 and <f, v_p> per column
-// half-tile instead of the features themselves): cos = <f, v> / (max(||f||, eps) max(||v||, eps)), then the reference's fp32
-// chain (cos+1)/2 and 1 - s.  One thread per (clip, prototype) row.  (The fused kernels form the cosine the same way.)
-__global__ void __launch_bounds__(256) proto_norms_kernel(const float* __restrict__ protos, int P, int D, float* __restrict__ vnorm) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * 8 + warp;
-  if (p >= P) return;
-  float vv = 0.f;
-  for (int d = lane; d < D; d += 32) { const float b = protos[(size_t)p * D + d]; vv = fmaf(b, b, vv); }
-  vv = warp_sum(vv);
-  if (lane == 0) vnorm[p] = fmaxf(sqrtf(vv), 1e-8f);
+// Prototype stage from per-row statistics: the GEMM that produced the pooled features left, per column half-tile,
+// (||f||^2, <f, v_p>, ||v_p||^2) over its columns instead of the features themselves.
+// cos = <f, v> / (max(||f||, eps) max(||v||, eps)), then the reference's fp32 chain (cos+1)/2 and 1 - s (the fused kernels form
+// the cosine the same way).
+__device__ __forceinline__ float sim_from_stats(const float4* sp, int nparts) {
+  float ff = 0.f, dot = 0.f, vv = 0.f;
+  for (int t = 0; t < nparts; ++t) { const float4 v = sp[t]; ff += v.x; dot += v.y; vv += v.z; }
+  const float cosv = dot / (fmaxf(sqrtf(ff), 1e-8f) * fmaxf(sqrtf(vv), 1e-8f));
+  return (cosv + 1.0f) / 2.0f;
 }
-__global__ void __launch_bounds__(256) proto_from_stats_kernel(const float* __restrict__ stat, int nparts, const float* __restrict__ vnorm,
-                                                               long long rows, int P, float* __restrict__ sim, float* __restrict__ dist) {
+// thousands of prototypes: one thread per (clip, prototype) row, the logits by proto_logits_wide_kernel
+__global__ void __launch_bounds__(256) proto_from_stats_kernel(const float* __restrict__ stat, int nparts, long long rows,
+                                                               float* __restrict__ sim, float* __restrict__ dist) {
   pdl_launch_dependents();
   pdl_wait();
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const float2* sp = reinterpret_cast<const float2*>(stat) + (size_t)r * nparts;
-  float ff = 0.f, dot = 0.f;
-  for (int t = 0; t < nparts; ++t) { const float2 v = sp[t]; ff += v.x; dot += v.y; }
-  const float nf = fmaxf(sqrtf(ff), 1e-8f);
-  const float cosv = dot / (nf * vnorm[r % P]);
-  const float s = (cosv + 1.0f) / 2.0f;
+  const float s = sim_from_stats(reinterpret_cast<const float4*>(stat) + (size_t)r * nparts, nparts);
   sim[r] = s;
   if (dist) dist[r] = 1.0f - s;
+}
+// up to 1024 prototypes: one block per clip -- similarities into shared memory, then one warp per class for the logits
+__global__ void __launch_bounds__(PS_THREADS) proto_finish_stats_kernel(const float* __restrict__ stat, int nparts,
+                                                                        const float* __restrict__ last_layer, int N, int P, int K,
+                                                                        float* __restrict__ logits, float* __restrict__ sim,
+                                                                        float* __restrict__ dist) {
+  __shared__ float s_sim[1024];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    for (int pp = threadIdx.x; pp < P; pp += PS_THREADS) {
+      const size_t r = (size_t)n * P + pp;
+      const float s = sim_from_stats(reinterpret_cast<const float4*>(stat) + r * nparts, nparts);
+      s_sim[pp] = s;
+      sim[r] = s;
+      if (dist) dist[r] = 1.0f - s;
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += PS_WARPS) {
+      float acc = 0.f;
+      for (int pp = lane; pp < P; pp += 32) acc = fmaf(s_sim[pp], last_layer[(size_t)k * P + pp], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) logits[(size_t)n * K + k] = acc;
+    }
+    __syncthreads();
+  }
 }
 
 // best_vec[p,:] = feats[n*,p,:] where n* = clip of this call that holds best_key[p] (keys carry the global clip index);
@@ -258,21 +279,21 @@ int launch_proto_stage(const float* feats, const float* protos, const float* las
   return PASN_OK;
 }
 
-int launch_proto_norms(const float* protos, int P, int D, float* vnorm, cudaStream_t st) {
-  proto_norms_kernel<<<ceil_div(P, 8), 256, 0, st>>>(protos, P, D, vnorm);
-  PASN_LAUNCH_CHECK();
-  count_launch();
-  return PASN_OK;
-}
-int launch_proto_from_stats(const float* stat, int nparts, const float* vnorm, const float* last_layer, int N, int P, int K,
-                            float* logits, float* sim, float* dist, cudaStream_t st) {
+int launch_proto_from_stats(const float* stat, int nparts, const float* last_layer, int N, int P, int K, float* logits, float* sim,
+                            float* dist, cudaStream_t st) {
   if (N <= 0) return PASN_OK;
+  if (P <= 1024) {
+    if (launch_pdl(proto_finish_stats_kernel, dim3(N < 148 * 8 ? N : 148 * 8), dim3(PS_THREADS), 0, st, stat, nparts, last_layer, N, P, K,
+                   logits, sim, dist) != cudaSuccess)
+      return PASN_ERR_CUDA;
+    count_launch();
+    return PASN_OK;
+  }
   const long long rows = (long long)N * P;
-  if (launch_pdl(proto_from_stats_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, stat, nparts, vnorm, rows, P, sim, dist) !=
-      cudaSuccess)
+  if (launch_pdl(proto_from_stats_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, stat, nparts, rows, sim, dist) != cudaSuccess)
     return PASN_ERR_CUDA;
   count_launch();
-  if (P >= 1024 && (long long)N * K <= 148 * 64) {
+  if ((long long)N * K <= 148 * 64) {
     if (launch_pdl(proto_logits_wide_kernel, dim3(N * K), dim3(PS_THREADS), 0, st, sim, last_layer, N, P, K, logits) != cudaSuccess) return PASN_ERR_CUDA;
   } else {
     if (launch_pdl(proto_logits_kernel, dim3(N < 148 * 8 ? N : 148 * 8), dim3(PS_THREADS), 0, st, sim, last_layer, N, P, K, logits) != cudaSuccess)

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const float* rp = g.rowparts + ((size_t)b * g.M + row) * g.nparts;
         for (int j = 0; j < g.nparts; ++j) rowterm += rp[j];
       }
-      float psum = 0.f, st_ff = 0.f, st_dot = 0.f;
+      float psum = 0.f, st_ff = 0.f, st_dot = 0.f, st_vv = 0.f;
       if (has_vec && h < nh && m0 + q * 32 < g.M) {   // bias / colvec slices of this warp's groups -> per-warp smem, before the accumulator is due
         __syncwarp();
         for (int cg = 0; cg < ngroups; ++cg) {
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         if (lane == 0) acc_release(buf);
         if (psum_p != nullptr && row_ok) psum_p[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = 0.f;
         if (rowstat_p != nullptr && row_ok)
-          *reinterpret_cast<float2*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) = make_float2(0.f, 0.f);
+          *reinterpret_cast<float4*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
       }
       for (int cg = 0; cg < ngroups; ++cg) {
@@ -615,6 +615,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             st_ff = fmaf(v[4 * j4 + 1], v[4 * j4 + 1], st_ff); st_dot = fmaf(v[4 * j4 + 1], w4.y, st_dot);
             st_ff = fmaf(v[4 * j4 + 2], v[4 * j4 + 2], st_ff); st_dot = fmaf(v[4 * j4 + 2], w4.z, st_dot);
             st_ff = fmaf(v[4 * j4 + 3], v[4 * j4 + 3], st_ff); st_dot = fmaf(v[4 * j4 + 3], w4.w, st_dot);
+            st_vv = fmaf(w4.x, w4.x, fmaf(w4.y, w4.y, fmaf(w4.z, w4.z, fmaf(w4.w, w4.w, st_vv))));
           }
         } else if (rowstat_p != nullptr && row_ok) {   // ||row||^2 and <row, vector of this row's prototype> over this group's columns
           const float* vr = g.dotvec + (long long)(row % g.dot_mod) * g.dot_ld + col0;
@@ -626,11 +627,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
               st_ff = fmaf(v[4 * j4 + 1], v[4 * j4 + 1], st_ff); st_dot = fmaf(v[4 * j4 + 1], w4.y, st_dot);
               st_ff = fmaf(v[4 * j4 + 2], v[4 * j4 + 2], st_ff); st_dot = fmaf(v[4 * j4 + 2], w4.z, st_dot);
               st_ff = fmaf(v[4 * j4 + 3], v[4 * j4 + 3], st_ff); st_dot = fmaf(v[4 * j4 + 3], w4.w, st_dot);
+              st_vv = fmaf(w4.x, w4.x, fmaf(w4.y, w4.y, fmaf(w4.z, w4.z, fmaf(w4.w, w4.w, st_vv))));
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 64; ++j)
-              if (col0 + j < g.N) { st_ff = fmaf(v[j], v[j], st_ff); st_dot = fmaf(v[j], __ldg(vr + j), st_dot); }
+              if (col0 + j < g.N) { const float wv = __ldg(vr + j); st_ff = fmaf(v[j], v[j], st_ff); st_dot = fmaf(v[j], wv, st_dot); st_vv = fmaf(wv, wv, st_vv); }
           }
         }
         if (psum_p != nullptr) {
@@ -663,8 +665,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       if (w == 0 && lane == 0 && tv < 16) TCG_TRACE(32 + tv);   // this tile's rows are out of the registers
       if (psum_p != nullptr && row_ok) psum_p[((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw] = (split_out && hw == 1) ? 0.f : psum;
       if (rowstat_p != nullptr && row_ok)
-        *reinterpret_cast<float2*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 2) =
-            (split_out && hw == 1) ? make_float2(0.f, 0.f) : make_float2(st_ff, st_dot);
+        *reinterpret_cast<float4*>(rowstat_p + (((size_t)b * g.M + row) * (2 * kp.tiles_n) + 2 * tn + hw) * 4) =
+            (split_out && hw == 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(st_ff, st_dot, st_vv, 0.f);
     }
     if (w == 0 && lane == 0) { TCG_TRACE(8); TCG_TRACE1(13); }   // last tile's rows are out of the registers
     if (w == 4 && lane == 0) TCG_TRACE(12);
@@ -742,11 +744,11 @@ int launch(const Gemm& g, cudaStream_t st) {
     attr_done = true;
   }
   static const int pair_env = [] { const char* e = getenv("PASN_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // A/B switch
-  // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py); short-K GEMMs are bound by
-  // their epilogues and lose to the cross-CTA hand-offs: the launch trace (tools/trace_gemm.py) shows the partner CTA's
-  // last rows leaving 1.5-1.9 us after the leader's and the closing cluster barrier waiting for them -- ~3 us per launch,
-  // and the K = 512 GEMMs of the chain ran 4 us faster (of 64) on single CTAs.  Hence from 16 k-block passes per tile.
-  static const int pair_min = [] { const char* e = getenv("PASN_GEMM_PAIR_MIN"); return e ? atoi(e) : 16; }();
+  // pairs pay off when the main loop is long (big K: +10 % on square GEMMs, tools/bench_gemm.py), from 8 k-block passes per
+  // tile.  (With the generic epilogue the K = 512 GEMMs of the chain lost 4 us of 64 to pairs -- the partner CTA's last rows
+  // left 1.5-1.9 us after the leader's, tools/trace_gemm.py; with the lean epilogues pairs win there too: config 2 at
+  // N = 1024 0.194 -> 0.187 ms, config 5 at N = 32 0.822 -> 0.806 ms.)
+  static const int pair_min = [] { const char* e = getenv("PASN_GEMM_PAIR_MIN"); return e ? atoi(e) : 8; }();
   const bool pair = (pair_env >= 0 ? pair_env != 0 : (g.pair != 0 && ceil_div(g.K, BK) * g.npass >= pair_min)) && g.bn >= 128 && g.M > BM;
   // two pairs per cluster sharing the B tile by multicast (full-width tiles, at least two pair tiles along M).  Correct (unit
   // tests with PASN_GEMM_PAIR=1 PASN_GEMM_QUAD=1) but measured SLOWER than plain pairs -- 8192^3: 694 vs 1264 TFLOP/s, layer-1

@@ -59,8 +59,8 @@ struct Gemm {
   int pair;                      // 1: CTA pairs (cta_group::2): 256 x bn tiles, each CTA of a 2-CTA cluster loads its 128 rows of A
                                  // and half of the B tile -- a third less L2 -> SM traffic per flop (bn >= 128 only; else ignored)
   // optional per-row statistics of the final fp32 values (the prototype stage's reductions folded into the GEMM that produces
-  // the pooled features, so that those need not be written and read back): rowstat[(b*M + m) * 2*tiles_n + t][0..1] =
-  // (sum_n v^2, sum_n v * dotvec[(m % dot_mod) * dot_ld + n]) over the columns of column half-tile t
+  // the pooled features, so that those need not be written and read back): rowstat[(b*M + m) * 2*tiles_n + t][0..3] =
+  // (sum_n v^2, sum_n v * w, sum_n w^2, 0) with w = dotvec[(m % dot_mod) * dot_ld + n] over the columns of column half-tile t
   float* rowstat; const float* dotvec; long long dot_ld; int dot_mod;
   int dot_early;                 // dotvec is not written by the kernel in front on the stream: it may be read before that one has completed
 };

@@ -32,7 +32,7 @@ struct Plan {
   int Pp;                      // column pitch of one plane of the token-major occurrence values
   int bn_c, tiles_n_c;         // tile width / count along S of the O GEMM (psum parts = 2 * tiles_n_c)
   int nb;                      // clips per chunk
-  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, off_stat, off_vnorm, total;
+  size_t off_xt, off_y, off_g2, off_occ, off_psum, off_pool, off_f, off_fe, off_stat, total;
   int stat_parts;              // column half-tiles of the GEMM that produces features_extracted (row statistics per part)
 };
 
@@ -73,8 +73,7 @@ Plan make_plan(const pasn_dims& d) {
   p.off_f = take(p.w2_first ? (size_t)p.nb * S * ex * d.D * 2 : 0);
   p.off_fe = take((size_t)p.nb * d.P * d.D * 4);
   p.stat_parts = 2 * ceil_div(d.D, d.D >= 256 ? 256 : 128);
-  p.off_stat = take((size_t)p.nb * d.P * p.stat_parts * 8);
-  p.off_vnorm = take((size_t)d.P * 4);
+  p.off_stat = take((size_t)p.nb * d.P * p.stat_parts * 16);
   p.total = o + 256;
   return p;
 }
@@ -310,8 +309,6 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && (P >= 1024 || (P <= 64 && p.w2_first)))) && !occ_only &&
                           feats == nullptr && push == nullptr;
   float* STAT = reinterpret_cast<float*>(ws + p.off_stat);
-  float* VNORM = reinterpret_cast<float*>(ws + p.off_vnorm);
-  if (fuse_stats && (rc = launch_proto_norms(w.prototypes, P, D, VNORM, st))) return rc;
   const __nv_bfloat16* W13 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w13);
   const __nv_bfloat16* W4 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w4);
   const __nv_bfloat16* W5 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w5);
@@ -484,7 +481,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   }
   // ---- cosine / similarity / logits / distance / push keys (+ winner capture)
   if (fuse_stats)
-    return launch_proto_from_stats(STAT, p.stat_parts, VNORM, w.last_layer, nb, P, d.K, logits + (size_t)n0 * d.K, sim + (size_t)n0 * P,
+    return launch_proto_from_stats(STAT, p.stat_parts, w.last_layer, nb, P, d.K, logits + (size_t)n0 * d.K, sim + (size_t)n0 * P,
                                    dist ? dist + (size_t)n0 * P : nullptr, st);
   pasn_push_args pa;
   const pasn_push_args* pp = nullptr;

@@ -205,14 +205,14 @@ def test_rank1_term_and_psum():
 
 @pytest.mark.parametrize("pair", [0, 1])
 def test_row_statistics_without_an_output(pair):
-    """||row||^2 and <row, vector[row % mod]> of the fp32 result per column half-tile, with no output stored at all (the
+    """||row||^2, <row, vector[row % mod]> and ||vector||^2 of the fp32 result per column half-tile, with no output stored at all (the
     prototype stage's reductions folded into the GEMM that makes the pooled features)."""
     M, N, K, mod = 520, 512, 576, 40
     A, B = _bf(_rand((M, K), 21)), _bf(_rand((N, K), 22))
     bias = _rand((N,), 23)
     V = _rand((mod, N), 24)
     tiles_n = 2
-    stat = torch.full((M, 2 * tiles_n, 2), -1.0, device="cuda")
+    stat = torch.full((M, 2 * tiles_n, 4), -1.0, device="cuda")
     g = Gemm()
     g.A, g.lda, g.ka = A.data_ptr(), K, K
     g.B, g.ldb, g.kb = B.data_ptr(), K, K
@@ -224,6 +224,7 @@ def test_row_statistics_without_an_output(pair):
     Vr = V.double()[torch.arange(M, device="cuda") % mod]
     _close(stat[:, :, 0].sum(1), (ref * ref).sum(1), 1e-5)
     _close(stat[:, :, 1].sum(1), (ref * Vr).sum(1), 2e-5)
+    _close(stat[:, :, 2].sum(1), (Vr * Vr).sum(1), 1e-5)                 # ... and the vector's own squared norm
     for t in range(2 * tiles_n):                      # each entry covers its own 128 columns
         cols = slice(128 * t, 128 * t + 128)
         _close(stat[:, t, 0], (ref[:, cols] ** 2).sum(1), 1e-5)
@@ -237,7 +238,7 @@ def test_row_statistics_few_rows_per_batch_item(bn):
     A, B = _bf(_rand((batch, M, K), 31)), _bf(_rand((batch, N, K), 32))
     V = _rand((mod, N), 33)
     tiles_n = N // bn
-    stat = torch.full((batch, M, 2 * tiles_n, 2), -1.0, device="cuda")
+    stat = torch.full((batch, M, 2 * tiles_n, 4), -1.0, device="cuda")
     g = Gemm()
     g.A, g.lda, g.a_bs, g.a_batched, g.ka = A.data_ptr(), K, M * K, 1, K
     g.B, g.ldb, g.b_bs, g.b_batched, g.kb = B.data_ptr(), K, N * K, 1, K
@@ -248,6 +249,7 @@ def test_row_statistics_few_rows_per_batch_item(bn):
     ref = torch.bmm(A.double(), B.double().transpose(1, 2))
     _close(stat[..., 0].sum(2), (ref * ref).sum(2), 1e-5)
     _close(stat[..., 1].sum(2), (ref * V.double()[None]).sum(2), 2e-5)
+    _close(stat[..., 2].sum(2), (V.double() ** 2).sum(1)[None].expand(batch, M), 1e-5)
     half = bn // 2
     for t in range(2 * tiles_n):                      # each entry covers its own column half-tile
         cols = slice(half * t, half * t + half)
