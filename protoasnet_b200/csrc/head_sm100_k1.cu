@@ -70,8 +70,19 @@ __device__ __forceinline__ void split_points(int nkc, int& a1, int& a2) {  // wh
 
 }  // namespace
 
-template <int PP, bool TRACE>
+// Everything that is fixed per launch is a template parameter: the kernel is ~7 k instructions for five warp roles, and code
+// of orders / input kinds / experiments that do not run still spreads the ones that do over more instruction-cache lines
+// (ncu: 8 % of the issue slots lost to instruction fetch before; serial bf16 NCDHW instantiation 8256 -> ~5.5 k instructions).
+// IN: 0 = bf16 [N,C,S], 1 = bf16 channels_last [N,S,C], 2 = fp32 [N,C,S] (rounded to bf16 on the fly).
+#ifndef PASN_K1_EXPERIMENTS
+#define PASN_K1_EXPERIMENTS 0   // 1: the timing experiments of profiles/README.md (PASN_DBG_SKIP, PASN_X_DRAIN, PASN_FLUSH_SLEEP, ...)
+#endif
+template <int PP, bool TRACE, bool TWO_PHASE, int IN>
 __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Params p) {
+  constexpr bool nsc = IN == 1, f32_in = IN == 2;
+  const int dbg_skip = PASN_K1_EXPERIMENTS ? p.dbg_skip : 0, x_drain = PASN_K1_EXPERIMENTS ? p.x_drain : 0,
+            flush_sleep = PASN_K1_EXPERIMENTS ? p.flush_sleep : 0, flush_kmajor = PASN_K1_EXPERIMENTS ? p.flush_kmajor : 1,
+            l2_hints = PASN_K1_EXPERIMENTS ? p.l2_hints : 1;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   const int ntiles = (ntok + TILE_M - 1) / TILE_M;
   const PackedLayout PL = packed_layout(p.C);
   Ctx ctx{p.err, abort_s, p.fault, p.spin};
-  const bool two_phase = p.phases != 1;
+  constexpr bool two_phase = TWO_PHASE;   // (compile-time: the serial order's kernel is 14 % smaller without the other order's code)
 
   if ((smem_u32(smem) & 1023u) != 0) {  // swizzled layouts need the 1024-byte alignment we asked for
     if (tid == 0) atomicCAS(p.err, 0, 900);
@@ -160,10 +171,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         if constexpr (TRACE) K1_TRACE(0, tile, slot);
       };
       // X tile: MN-major (voxels contiguous) for NCDHW input, K-major (channels contiguous) for channels_last input
-      const uint32_t x_mn = p.nsc ? 0u : 1u;
+      const uint32_t x_mn = nsc ? 0u : 1u;
       const uint32_t idesc_g = make_idesc_bf16(128, 256, x_mn, 0);    // A = X tile, B = W3 chunk (K-major)
       const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, x_mn);    // A = W1 half chunk (K-major), B = X tile
-      const uint32_t xk = p.nsc ? 2u : 128u;                          // descriptor advance per K step of 16 channels
+      const uint32_t xk = nsc ? 2u : 128u;                          // descriptor advance per K step of 16 channels
       const uint32_t idesc_g2 = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_pool = make_idesc_bf16(128, NPOOL, 0, 1);  // A = H1^T in TMEM, B = Os (MN-major, no swizzle)
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       constexpr uint32_t HI_SW128 = desc_hi(1024, SWZ_128B);   // X tile (MN-major) and weight images (K-major): SBO 1024
       constexpr uint32_t HI_OS = desc_hi(128, SWZ_NONE);       // Os: MN-major, no swizzle, SBO 128
       const uint32_t tb = tbase;
-      const uint32_t x_lo0 = desc_lo(x_base, p.nsc ? 16u : 8192u), w_lo0 = desc_lo(w_base, 16), os_lo0 = desc_lo(os_base, lbo_os);
+      const uint32_t x_lo0 = desc_lo(x_base, nsc ? 16u : 8192u), w_lo0 = desc_lo(w_base, 16), os_lo0 = desc_lo(os_base, lbo_os);
       const uint32_t bar0 = smem_u32(bars);
       auto baddr = [&](int b) -> uint32_t { return bar0 + 8u * (uint32_t)b; };
       const uint32_t njobs = (uint32_t)ntiles * (uint32_t)nkc * (two_phase ? 2u : 1u);
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           constexpr int SKEW = XSLOTS - (XDEPTH - 1) < 3 ? XSLOTS - (XDEPTH - 1) : 3;
           // (only for channels_last input: the NCDHW gather is the slower one and does not like waiting for two chunks
           // before the add-on block of the first -- measured 159.6 vs 157.3 us -- while channels_last gains 2-4 %)
-          const int skew = !p.nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
+          const int skew = !nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
           for (int kc = 0; kc < k_skew && ok; ++kc) {
             long long tc0 = 0;
             if constexpr (TRACE) tc0 = clock64();
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const uint32_t ws = wst % WSLOTS, wph = (wst / WSLOTS) & 1;
         ++wst;
         if (!bwait(&bars[B_WEMPTY + ws], wph ^ 1, ctx, 201)) return false;
-        if (p.dbg_skip & 1) { mbar_arrive(&bars[B_WFULL + ws]); return true; }
+        if (dbg_skip & 1) { mbar_arrive(&bars[B_WFULL + ws]); return true; }
         mbar_arrive_expect_tx(&bars[B_WFULL + ws], bytes);
         for (uint32_t o = 0; o < bytes; o += 16384)
           bulk_g2s(w_base + ws * WSLOT_BYTES + o, p.packed + src + o, 16384, &bars[B_WFULL + ws]);
@@ -452,7 +463,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           }
         } else {
           constexpr int SKEW = XSLOTS - (XDEPTH - 1) < 3 ? XSLOTS - (XDEPTH - 1) : 3;
-          const int skew = !p.nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
+          const int skew = !nsc ? 0 : (nkc < SKEW ? nkc : SKEW), k_skew = nkc - skew;
           for (int kc = 0; kc < k_skew && ok; ++kc)
             ok = put(PL.off_l1 + (size_t)(2 * kc) * 32768, 32768) && put(PL.off_l1 + (size_t)(2 * kc + 1) * 32768, 32768);
           for (int kc = k_skew; kc < nkc && ok; ++kc) ok = put(PL.off_l1 + (size_t)(2 * kc) * 32768, 32768);
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
     // issued ones by XDEPTH - 1).  The decision is made by lane 0 and broadcast: the publish protocol is warp-collective.
     auto slot_free_or_drain = [&](uint32_t g, uint32_t xs, uint32_t xph, uint32_t& pub) -> bool {
       const uint32_t full = __shfl_sync(0xffffffffu, mbar_test_wait(&bars[B_XEMPTY + xs], xph ^ 1) ? 0u : 1u, 0);
-      if (full && p.x_drain) {
+      if (full && x_drain) {
         if (pub < g) {
           cp_async_wait<0>();
           while (pub < g) {
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
       }
       return bwait(&bars[B_XEMPTY + xs], xph ^ 1, ctx, 301);
     };
-    if (p.nsc) {
+    if (nsc) {
       // channels_last feature map [N][S][C]: a voxel's 64 channels of a chunk are 128 contiguous, 16-byte aligned bytes,
       // i.e. one row of the K-major SWIZZLE_128B operand image.  16-byte L1-bypassing cp.async: eight lanes per voxel row,
       // four rows per warp instruction, 32 rows per warp.  Voxels of consecutive clips are contiguous in this layout.
@@ -514,7 +525,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int row = xw * 32 + j * 4 + r4;
-          const bool valid = tile * TILE_M + row < ntok && !(p.dbg_skip & 2);
+          const bool valid = tile * TILE_M + row < ntok && !(dbg_skip & 2);
           cp_async_16(dst0 + off_kmajor_sw128(row, sub * 8), src0 + (size_t)(valid ? row : 0) * p.C, valid ? 16u : 0u);
         }
         cp_async_commit();
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         cp_async_wait<0>();
         while (pub < njobs) publish();
       }
-    } else if (!p.f32_in) {
+    } else if (!f32_in) {
       const uint64_t pol_first = l2_policy_evict_first();
       uint32_t pub = 0;
       auto publish = [&]() {
@@ -542,14 +553,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         const int tile = (int)(g / jobs_per_tile);
         const int kc = (int)((g - (uint32_t)tile * jobs_per_tile) % (uint32_t)nkc);
         const int t = tile * TILE_M + 4 * lane;
-        const bool valid = t < ntok && !(p.dbg_skip & 2);
+        const bool valid = t < ntok && !(dbg_skip & 2);
         const int clipl = valid ? t / S : 0;
         const int s = valid ? t - clipl * S : 0;
         // virtual clip -> (real clip, voxel group): rows of the feature map keep the real pitch SR
         const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
         const __nv_bfloat16* src = p.feat + ((size_t)rc * p.C + kc * 64 + xw * 16) * p.SR + (size_t)vg * S + s;
         const uint32_t dst0 = x_base + xs * XSLOT_BYTES;
-        if (p.l2_hints) {
+        if (l2_hints) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             cp_async_8_hint(dst0 + off_mnmajor_sw128(4 * lane, xw * 16 + j, 8192), src + (size_t)j * p.SR, valid ? 8u : 0u, pol_first);
@@ -629,7 +640,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
             const int vc = c_begin + clipl, rc = vc / p.G, vg = vc - rc * p.G;
             const size_t o0 = ((size_t)rc * p.P) * p.SR + (size_t)vg * S + s;
             const unsigned char* src = os + off_mnmajor_nosw(slot * PP, tok, NPOOL);
-            if (!p.f32_in) {
+            if (!f32_in) {
               __nv_bfloat16* orow = p.occ + o0;
 #pragma unroll 8
               for (int pp = 0; pp < p.P; ++pp)
@@ -872,7 +883,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         for (int rep = 0; rep < 2; ++rep) {
           const bool flush = rep == 0 ? boundary : ends;
           if (!flush) continue;
-          if (p.dbg_skip & 8) {   // timing experiment: no hi/lo split, no stores (results garbage)
+          if (dbg_skip & 8) {   // timing experiment: no hi/lo split, no stores (results garbage)
             if (lane == 0) red_release_gpu_add(p.ready + c_begin + (rep == 0 ? first_clip : last_clip), 1);
             if (rep == 0) {
 #pragma unroll
@@ -887,7 +898,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           const int tile2 = clip / p.cpt;
           const int rowb = (clip - tile2 * p.cpt) * PP;
           uint8_t* img = p.feimg + (size_t)tile2 * FE_TILE_BYTES + (size_t)(d >> 6) * 16384;
-          if (p.flush_kmajor) {
+          if (flush_kmajor) {
             // K2's A operand K-major (row = (clip,p), k = d contiguous): the 32 lanes of a warp hold 32 consecutive d of
             // one row, i.e. 64 bytes inside one 128-byte swizzle row -> one line per warp store (hi at +0, lo at +64 KB)
 #pragma unroll
@@ -896,7 +907,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
               const __nv_bfloat16 h = __float2bfloat16_rn(v);
               const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
               const uint32_t off = off_kmajor_sw128(rowb + j, d & 63);
-              if (p.l2_hints) {
+              if (l2_hints) {
                 st_global_u16_hint(img + off, __bfloat16_as_ushort(h), pol_last);
                 st_global_u16_hint(img + 65536 + off, __bfloat16_as_ushort(l), pol_last);
               } else {
@@ -905,7 +916,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
               }
               // the burst of 2*PP stores per thread competes with the feature gather of the next tile's first chunks
               // for the load/store path; these warps have nothing to do until that tile's layer 1 is done, so pace it
-              if (p.flush_sleep && (j & 3) == 3) __nanosleep(p.flush_sleep);
+              if (flush_sleep && (j & 3) == 3) __nanosleep(flush_sleep);
             }
           } else {
             // K2's A operand MN-major (row = (clip,p) contiguous, k = d): this thread's PP values for its d are
@@ -952,22 +963,27 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
   }
 }
 
-template <int PP, bool TRACE>
+template <int PP, bool TRACE, bool TWO_PHASE, int IN>
 static int launch_inst(const K1Params& k1, int grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(head_tokens2_kernel<PP, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(head_tokens2_kernel<PP, TRACE, TWO_PHASE, IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM) != cudaSuccess)
       return PASN_ERR_CUDA;
     attr_done = true;
   }
-  head_tokens2_kernel<PP, TRACE><<<grid, K1_THREADS, K1_SMEM, st>>>(k1);
+  head_tokens2_kernel<PP, TRACE, TWO_PHASE, IN><<<grid, K1_THREADS, K1_SMEM, st>>>(k1);
   PASN_LAUNCH_CHECK();
   return PASN_OK;
 }
 template <int PP>
 static int launch_one(const K1Params& k1, int grid, cudaStream_t st) {
-  // the instrumented instantiation (clock reads on the issue path) only runs while a trace buffer is installed
-  return k1.trace != nullptr ? launch_inst<PP, true>(k1, grid, st) : launch_inst<PP, false>(k1, grid, st);
+  // The instrumented instantiation (clock reads on the issue path) only runs while a trace buffer is installed.  The
+  // two-phase order (an A/B variant, slower) and the trace exist for bf16 maps; fp32 maps always run the plain serial kernel.
+  const bool tr = k1.trace != nullptr;
+  if (k1.f32_in) return launch_inst<PP, false, false, 2>(k1, grid, st);
+  if (k1.nsc) return tr ? launch_inst<PP, true, false, 1>(k1, grid, st) : launch_inst<PP, false, false, 1>(k1, grid, st);
+  if (k1.phases != 1) return tr ? launch_inst<PP, true, true, 0>(k1, grid, st) : launch_inst<PP, false, true, 0>(k1, grid, st);
+  return tr ? launch_inst<PP, true, false, 0>(k1, grid, st) : launch_inst<PP, false, false, 0>(k1, grid, st);
 }
 
 int launch_k1_two_phase(const K1Params& k1, int ppad, int grid, cudaStream_t st) {
