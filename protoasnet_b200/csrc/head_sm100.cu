@@ -580,7 +580,6 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   float* osum = reinterpret_cast<float*>(wsp + L.off_osum);
   int* err = reinterpret_cast<int*>(wsp + L.off_err);
   int* ready = reinterpret_cast<int*>(wsp + L.off_ready);
-  if (cudaMemsetAsync(err, 0, 256 + (size_t)L.Nv * 4, st) != cudaSuccess) return PASN_ERR_CUDA;
 
   static const int num_sms = [] {
     int dev = 0, n = 0;
@@ -604,8 +603,8 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.fault = fault_word();
   k1.trace = g_trace;
   { const char* e = getenv("PASN_DBG_SKIP"); k1.dbg_skip = e ? atoi(e) : 0; }
-  static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return e ? atoi(e) : 1; }();
-  static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return e ? atoi(e) : 1; }();
+  static const int flush_kmajor = [] { const char* e = getenv("PASN_FLUSH_KMAJOR"); return (PASN_K1_EXPERIMENTS && e) ? atoi(e) : 1; }();
+  static const int l2_hints = [] { const char* e = getenv("PASN_L2_HINTS"); return (PASN_K1_EXPERIMENTS && e) ? atoi(e) : 1; }();
   k1.flush_kmajor = flush_kmajor; k1.l2_hints = l2_hints;
   static const int x_drain = [] { const char* e = getenv("PASN_X_DRAIN"); return e ? atoi(e) : 0; }();
   k1.x_drain = x_drain;
@@ -613,8 +612,13 @@ int sm100_head_forward(const void* feat, const pasn_weights& w, const void* pack
   k1.spin = spin;
   static const int flush_sleep = [] { const char* e = getenv("PASN_FLUSH_SLEEP"); return e ? atoi(e) : 0; }();
   k1.flush_sleep = flush_sleep;
-  static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return e ? atoi(e) : 0; }();
-  k1.ready = ready;
+  // clip-level hand-off to the prototype kernel: an experiment (measured slower), only in builds with -DPASN_K1_EXPERIMENTS=1
+  static const int k2_early = [] { const char* e = getenv("PASN_K2_EARLY"); return (PASN_K1_EXPERIMENTS && e) ? atoi(e) : 0; }();
+  k1.ready = k2_early ? ready : nullptr;
+  // The workspace's error word (what pasn_debug_sm100_error reads; faults themselves go to the sticky fault word) and the
+  // hand-off counters are only cleared when somebody will look at them: a memset in front of every call is ~2 us of the step.
+  static const int dbg_sync = [] { const char* e = getenv("PASN_DEBUG_SYNC"); return e ? atoi(e) : 0; }();
+  if ((k2_early || dbg_sync) && cudaMemsetAsync(err, 0, 256 + (size_t)L.Nv * 4, st) != cudaSuccess) return PASN_ERR_CUDA;
   const int grid1 = ceil_div(L.Nv, k1.clips_per_cta);
   const int ppad = (d.P + 7) / 8 * 8;
   // Token-kernel tile orders (same results; profiles/README.md): 1 = serial (default), 2 = two-phase

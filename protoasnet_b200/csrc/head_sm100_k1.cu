@@ -74,9 +74,6 @@ __device__ __forceinline__ void split_points(int nkc, int& a1, int& a2) {  // wh
 // of orders / input kinds / experiments that do not run still spreads the ones that do over more instruction-cache lines
 // (ncu: 8 % of the issue slots lost to instruction fetch before; serial bf16 NCDHW instantiation 8256 -> ~5.5 k instructions).
 // IN: 0 = bf16 [N,C,S], 1 = bf16 channels_last [N,S,C], 2 = fp32 [N,C,S] (rounded to bf16 on the fly).
-#ifndef PASN_K1_EXPERIMENTS
-#define PASN_K1_EXPERIMENTS 0   // 1: the timing experiments of profiles/README.md (PASN_DBG_SKIP, PASN_X_DRAIN, PASN_FLUSH_SLEEP, ...)
-#endif
 template <int PP, bool TRACE, bool TWO_PHASE, int IN>
 __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Params p) {
   constexpr bool nsc = IN == 1, f32_in = IN == 2;
@@ -683,14 +680,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
         if (lane + 32 < p.P) p.osum[(size_t)(c_begin + first_clip) * p.P + lane + 32] = acc1;
         acc0 = s0[1]; acc1 = s1[1];
         __syncwarp();
-        if (lane == 0) red_release_gpu_add(p.ready + c_begin + first_clip, 1);
+        if (PASN_K1_EXPERIMENTS && p.ready != nullptr && lane == 0) red_release_gpu_add(p.ready + c_begin + first_clip, 1);
       }
       if ((last_tok + 1) % S == 0) {
         if (lane < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane] = acc0;
         if (lane + 32 < p.P) p.osum[(size_t)(c_begin + last_clip) * p.P + lane + 32] = acc1;
         acc0 = acc1 = 0.f;
         __syncwarp();
-        if (lane == 0) red_release_gpu_add(p.ready + c_begin + last_clip, 1);
+        if (PASN_K1_EXPERIMENTS && p.ready != nullptr && lane == 0) red_release_gpu_add(p.ready + c_begin + last_clip, 1);
       }
     }
   } else if (warp >= W_EPI0) {
@@ -884,7 +881,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           const bool flush = rep == 0 ? boundary : ends;
           if (!flush) continue;
           if (dbg_skip & 8) {   // timing experiment: no hi/lo split, no stores (results garbage)
-            if (lane == 0) red_release_gpu_add(p.ready + c_begin + (rep == 0 ? first_clip : last_clip), 1);
+            if (PASN_K1_EXPERIMENTS && p.ready != nullptr && lane == 0) red_release_gpu_add(p.ready + c_begin + (rep == 0 ? first_clip : last_clip), 1);
             if (rep == 0) {
 #pragma unroll
               for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);
@@ -938,7 +935,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) head_tokens2_kernel(const K1Par
           }
           // hand the clip to the prototype kernel (it polls the counter; see proto_w2_kernel)
           __syncwarp();
-          if (lane == 0) red_release_gpu_add(p.ready + clip, 1);
+          if (PASN_K1_EXPERIMENTS && p.ready != nullptr && lane == 0) red_release_gpu_add(p.ready + clip, 1);
           if (rep == 0) {
 #pragma unroll
             for (int j = 0; j < PP; ++j) facc[j] = __uint_as_float(nb[j]);

@@ -63,6 +63,12 @@ struct K1Params {
   int spin;                    // Ctx::spin
 };
 
+// 1: build the timing experiments of profiles/README.md into the fused kernels (PASN_DBG_SKIP, PASN_X_DRAIN, PASN_FLUSH_SLEEP,
+// PASN_FLUSH_KMAJOR, PASN_L2_HINTS, PASN_K2_EARLY); 0 (the product build): those switches are constants and their code is gone
+#ifndef PASN_K1_EXPERIMENTS
+#define PASN_K1_EXPERIMENTS 0
+#endif
+
 struct Ctx {
   int* err;
   volatile int* abort_s;
