@@ -10,6 +10,8 @@ python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 > gpurun_out/${R}_be
 python tools/bench_configs.py > gpurun_out/${R}_bench_configs.txt 2>&1
 python tools/bench_gemm.py > gpurun_out/${R}_bench_gemm.txt 2>&1
 python tools/time_backward.py > gpurun_out/${R}_time_backward.txt 2>&1
+python tools/trace_gemm.py cfg2_image 1024 bf16 > gpurun_out/${R}_gemm_trace_cfg2.txt 2>&1
+python tools/probe_chain_gemms.py 15 > gpurun_out/${R}_probe_chain_gemms.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${R}_ncu_launches_bench.csv python bench.py --steps 20 --warmup 5 --no-push > gpurun_out/ncu_bench.log 2>&1
 for c in "cfg2_image 1024 bf16" "cfg5_scaled 32 bf16" "cfg3_video_b1024 1024 fp32"; do set -- $c; ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_ncu_launches_$1_$3.csv python tools/run_cfg.py $1 $2 $3 2 > /dev/null 2>&1; done
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_ncu_launches_backward_fp32.csv python tools/run_bwd.py 256 fp32 > /dev/null 2>&1
