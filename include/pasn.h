@@ -223,7 +223,9 @@ float pasn_debug_last_main_kernel_ms(void);
 int pasn_debug_fault(void);
 int pasn_debug_set_fault(int code);
 /* synchronises `stream` and returns the bounded-wait error code the fused tcgen05 kernels left in `workspace`
- * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid) */
+ * on the last pasn_head_forward with these dims (0 = none; non-zero = internal pipeline fault, results invalid).  The word is
+ * only cleared in front of a call when the process runs with PASN_DEBUG_SYNC=1 (a memset per call otherwise costs ~2 us of a
+ * 170 us step); without it read pasn_debug_fault(), the sticky fault word every bounded wait reports into. */
 int pasn_debug_sm100_error(const void* workspace, const pasn_dims* dims, void* stream);
 /* device buffer of 1024 int64: [0,768) clock64() stamps of CTA 0 of the token kernel per tile phase, [768,1024) globaltimer
  * stamps of the token kernel start/end and of CTA 0 of the prototype kernel (tools/trace_k1.py, trace_k2.py; NULL = off) */
