@@ -302,6 +302,10 @@ def main():
 
     # ---------------- device-resident head forward ----------------
     with torch.no_grad():
+        # ranks leave their set-up (imports, weights, NCCL) seconds apart: line them up BEFORE the warm-up, otherwise the early
+        # ones sit idle at the timed region's barrier until their clocks have dropped, and the 20 timed steps (3.4 ms) are
+        # run on a GPU that is still ramping up (2- and 4-GPU records of round 2: 216 / 248 us per step against 172 on one)
+        barrier()
         for _ in range(args.warmup):
             model(x)
         l0 = lib.pasn_debug_launch_count()
@@ -384,6 +388,7 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     pipe = HostPipeline(model, chunks=4)
     with torch.no_grad():
+        barrier()   # (pinning the host buffers takes a different time on every rank)
         for _ in range(2):
             x_dev.copy_(x_host, non_blocking=True)
             model(x_dev)
