@@ -120,18 +120,30 @@ __device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, int* err, 
 
 }  // namespace
 
-// EPI selects how much of the epilogue is compiled in.  The generic epilogue (EPI_FULL) is ~10 k instructions of unrolled
-// 64-element loops behind launch-uniform branches; a tile's path through it jumps from one cold instruction-cache line to the
-// next (ncu: 20-30 % of the short GEMMs' issue slots lost to stall_no_inst).  The two shapes that carry the forward chain get
-// their own lean instantiations: EPI_LEAN = bias / rank-1 term / activation and TMA-stored outputs only, EPI_STAT = no output
-// at all, row statistics only.
-enum { EPI_FULL = 0, EPI_LEAN = 1, EPI_STAT = 2, EPI_DIRECT = 3 };   // EPI_DIRECT = EPI_LEAN + plain stores / two outputs split between the warp groups
+// EPI says how much of the epilogue is compiled in (a bit per feature).  The generic epilogue (EPI_FULL) is ~10 k
+// instructions of unrolled 64-element loops behind launch-uniform branches; a tile's path through it jumps from one cold
+// instruction-cache line to the next (ncu: 20-30 % of the short GEMMs' issue slots lost to stall_no_inst).  The shapes that
+// carry the chains get their own lean instantiations; launch() picks the first one that covers what the descriptor asks for.
+enum {
+  E_BIT_AUX = 1,      // element-wise epilogue inputs (addin / signin / mask: the backward)
+  E_BIT_PSUM = 2,     // row sums per column half-tile
+  E_BIT_STAT = 4,     // row statistics
+  E_BIT_DIRECT = 8,   // plain stores (unaligned / channel-major outputs), two outputs split between the warp groups
+  E_BIT_OUT = 16,     // any output at all
+  E_BIT_ABSOUT = 32,  // |value| on the second output
+  EPI_FULL = 63,
+  EPI_LEAN = E_BIT_OUT,                   // bias / rank-1 term / activation, TMA-stored outputs
+  EPI_STAT = E_BIT_STAT,                  // no output, row statistics only
+  EPI_DIRECT = E_BIT_OUT | E_BIT_DIRECT,
+  EPI_PSUM = E_BIT_OUT | E_BIT_PSUM,
+  EPI_AUX = E_BIT_OUT | E_BIT_AUX,
+};
 template <int MODE, int EPI>   // MODE 0: one CTA per tile, 1: CTA pairs, 2: two pairs per cluster sharing the B tile by multicast
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ KParams kp) {
   constexpr bool PAIR = MODE >= 1, QUAD = MODE == 2;
-  constexpr bool E_AUX = EPI == EPI_FULL, E_PSUM = EPI == EPI_FULL, E_STAT = EPI == EPI_FULL || EPI == EPI_STAT,
-                 E_DIRECT = EPI == EPI_FULL || EPI == EPI_DIRECT, E_OUT = EPI != EPI_STAT, E_ABSOUT = EPI == EPI_FULL,
-                 E_SPLIT = EPI == EPI_FULL || EPI == EPI_DIRECT;
+  constexpr bool E_AUX = (EPI & E_BIT_AUX) != 0, E_PSUM = (EPI & E_BIT_PSUM) != 0, E_STAT = (EPI & E_BIT_STAT) != 0,
+                 E_DIRECT = (EPI & E_BIT_DIRECT) != 0, E_OUT = (EPI & E_BIT_OUT) != 0, E_ABSOUT = (EPI & E_BIT_ABSOUT) != 0,
+                 E_SPLIT = E_DIRECT;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC);
@@ -738,7 +750,9 @@ int launch(const Gemm& g, cudaStream_t st) {
     const void* fns[] = {(const void*)tc_gemm_kernel<0, EPI_FULL>, (const void*)tc_gemm_kernel<1, EPI_FULL>, (const void*)tc_gemm_kernel<2, EPI_FULL>,
                          (const void*)tc_gemm_kernel<0, EPI_LEAN>, (const void*)tc_gemm_kernel<1, EPI_LEAN>,
                          (const void*)tc_gemm_kernel<0, EPI_STAT>, (const void*)tc_gemm_kernel<1, EPI_STAT>,
-                         (const void*)tc_gemm_kernel<0, EPI_DIRECT>, (const void*)tc_gemm_kernel<1, EPI_DIRECT>};
+                         (const void*)tc_gemm_kernel<0, EPI_DIRECT>, (const void*)tc_gemm_kernel<1, EPI_DIRECT>,
+                         (const void*)tc_gemm_kernel<0, EPI_PSUM>, (const void*)tc_gemm_kernel<1, EPI_PSUM>,
+                         (const void*)tc_gemm_kernel<0, EPI_AUX>, (const void*)tc_gemm_kernel<1, EPI_AUX>};
     for (const void* f : fns)
       if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return PASN_ERR_CUDA;
     attr_done = true;
@@ -841,26 +855,34 @@ int launch(const Gemm& g, cudaStream_t st) {
     cfg.attrs = at; cfg.numAttrs = na;
     // the leanest epilogue that can do what this launch asks for
     static const int epi_env = [] { const char* e = getenv("PASN_GEMM_EPI"); return e ? atoi(e) : 1; }();   // 0: always the generic one
-    bool any_out = false, all_tma = true, plain = true;
+    int need = 0;
     for (int mi = 0; mi < 2; ++mi) {
       if (g.out[mi].mode == OUT_NONE) continue;
-      any_out = true;
-      if (!kp.out_tma[mi]) all_tma = false;
-      if (g.out[mi].absval) plain = false;
+      need |= E_BIT_OUT;
+      if (!kp.out_tma[mi]) need |= E_BIT_DIRECT;
+      if (g.out[mi].absval) need |= E_BIT_ABSOUT;
     }
-    if (g.addin.ptr || g.signin.ptr || g.mask.ptr || g.psum) plain = false;
-    if (g.bn == 64 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE) all_tma = false;   // two outputs split between the warp groups
+    if (g.bn == 64 && g.out[0].mode != OUT_NONE && g.out[1].mode != OUT_NONE) need |= E_BIT_DIRECT;   // split between the warp groups
+    if (g.addin.ptr || g.signin.ptr || g.mask.ptr) need |= E_BIT_AUX;
+    if (g.psum) need |= E_BIT_PSUM;
+    if (g.rowstat) need |= E_BIT_STAT;
+    // (EPI_AUX: fwd+bwd of 256 clips 1.09-1.10 -> 1.06-1.07 ms; at 64 clips the step is launch-bound and moves with the box)
+    static const int aux_env = [] { const char* e = getenv("PASN_GEMM_EPI_AUX"); return e ? atoi(e) : 1; }();
+    static const int variants[] = {EPI_LEAN, EPI_STAT, EPI_DIRECT, EPI_PSUM, EPI_AUX};
     int epi = EPI_FULL;
-    if (epi_env && !quad && plain) {
-      if (g.rowstat == nullptr) epi = all_tma ? EPI_LEAN : EPI_DIRECT;
-      else if (!any_out) epi = EPI_STAT;
-    }
+    if (epi_env && !quad)
+      for (int v : variants)
+        if ((v & need) == need && (v != EPI_AUX || aux_env)) { epi = v; break; }
     cudaError_t e;
+#define TCG_LAUNCH(EPI_) (pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_>, kp))
     if (quad) e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<2, EPI_FULL>, kp);
-    else if (epi == EPI_LEAN) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_LEAN>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_LEAN>, kp);
-    else if (epi == EPI_DIRECT) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_DIRECT>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_DIRECT>, kp);
-    else if (epi == EPI_STAT) e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_STAT>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_STAT>, kp);
-    else e = pair ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1, EPI_FULL>, kp) : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0, EPI_FULL>, kp);
+    else if (epi == EPI_LEAN) e = TCG_LAUNCH(EPI_LEAN);
+    else if (epi == EPI_STAT) e = TCG_LAUNCH(EPI_STAT);
+    else if (epi == EPI_DIRECT) e = TCG_LAUNCH(EPI_DIRECT);
+    else if (epi == EPI_PSUM) e = TCG_LAUNCH(EPI_PSUM);
+    else if (epi == EPI_AUX) e = TCG_LAUNCH(EPI_AUX);
+    else e = TCG_LAUNCH(EPI_FULL);
+#undef TCG_LAUNCH
     if (e != cudaSuccess) return PASN_ERR_CUDA;
   }
   PASN_LAUNCH_CHECK();
