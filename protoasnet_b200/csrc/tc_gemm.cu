@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
               const uint32_t da = dst + (uint32_t)u * A_BYTES;
               if (!g.a_mn_major) {
                 tma_load(da, &kp.tmA, g.a_off[pass] + kb * BK, mu, g.a_batched ? b : 0, &bars[B_FULL + s]);
+              } else if (g.group > 1) {   // block-diagonal: item b*group + kb, its rows shifted to [kb*group_rows, ...)
+                for (int j = 0; j < 2; ++j)
+                  tma_load(da + j * 8192, &kp.tmA, g.a_off[pass] + 64 * j - g.group_rows * kb, 0, b * g.group + kb, &bars[B_FULL + s]);
               } else {
                 for (int j = 0; j < 2; ++j)
                   tma_load(da + j * 8192, &kp.tmA, g.a_off[pass] + mu + 64 * j, krow, (g.a_batched && !split_k) ? b : 0,
@@ -261,6 +264,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                    (g.b_batched && !split_k) ? b : 0, &bars[B_FULL + s], mc);
             } else if (!g.b_mn_major) {
               tma_load(dst + a_stage, &kp.tmB, g.b_off[pass] + kb * BK, n0, g.b_batched ? b : 0, &bars[B_FULL + s]);
+            } else if (g.group > 1) {
+              for (int j = 0; j < bnl / 64; ++j)
+                tma_load(dst + a_stage + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, 0, b * g.group + kb, &bars[B_FULL + s]);
             } else {
               for (int j = 0; j < bnl / 64; ++j)
                 tma_load(dst + a_stage + j * 8192, &kp.tmB, g.b_off[pass] + n0 + 64 * j, krow,
@@ -352,7 +358,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const int ngroups = half_cols / 64;
     uint32_t nstores = 0;   // TMA stores issued by this warp so far (slab = nstores & 1)
     // row statistics with the vectors' slices cached in the staging slabs (see below)
-    const bool stat_cached = !PAIR && rowstat_p != nullptr && !kp.out_tma[0] && !kp.out_tma[1] && g.M <= 64 && kp.tiles_m == 1 &&
+    const bool stat_cached = !PAIR && rowstat_p != nullptr && !kp.out_tma[0] && !kp.out_tma[1] && kp.tiles_m == 1 &&
+                             (g.M <= 64 || (g.M <= BM && ngroups == 1)) &&   // second column group in the idle row groups' slabs
                              nh == 2 && (g.N & 63) == 0 && (g.dot_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dotvec) & 15) == 0;
     int stat_key0 = -1, stat_key1 = -1;
     // slice of the vectors for this warp's rows and one column group -> slab(s); the row pairs are walked from a different
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       }
       __syncwarp();
     };
-    if (stat_cached && q < 2 && tile0 < ntiles) {   // the first tile's slices, while its operands are still on their way
+    if (stat_cached && q * 32 < g.M && tile0 < ntiles) {   // the first tile's slices, while its operands are still on their way
       const int n00 = ((tile0 % tiles_per_batch) % kp.tiles_n) * bn + hw * half_cols;
       stat_fill(0, n00);
       stat_key0 = n00;
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
       const int m0 = (r / kp.tiles_n) * BMT + (tv % nu) * BMC + (int)pq * BMP + (int)rank * BM, n0 = tn * bn;
       const uint32_t buf = i & 1;
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < g.M;
+      const bool row_ok = row < g.M && (g.stat_rows == 0 || (long long)b * g.M + row < g.stat_rows);
       float rowterm = 0.f;
       if (g.rowparts != nullptr && row_ok) {
         const float* rp = g.rowparts + ((size_t)b * g.M + row) * g.nparts;
@@ -790,6 +797,13 @@ int launch(const Gemm& g, cudaStream_t st) {
   kp.tiles_m = ceil_div(g.M, cl * BM * (tall ? 2 : 1));
   kp.tiles_n = ceil_div(g.N, g.bn);
   kp.nkb = ceil_div(g.K, BK);
+  if (g.group > 1) {
+    if (!(g.a_mn_major && g.b_mn_major && g.a_batched && g.b_batched) || g.npass != 1 || g.K > BK || g.k_rows_per_batch > 0 ||
+        g.M > BM || g.group * g.group_rows != g.M || g.group_items <= 0 || g.out[0].mode != OUT_NONE || g.out[1].mode != OUT_NONE ||
+        g.rowstat == nullptr || pair)
+      return PASN_ERR_INVALID;
+    kp.nkb = g.group;   // one k-block per item of the group
+  }
   const bool split_k = g.k_rows_per_batch > 0;
   if (split_k && !(g.a_mn_major && g.b_mn_major)) return PASN_ERR_INVALID;
   if (!g.a_mn_major) {
@@ -798,7 +812,7 @@ int launch(const Gemm& g, cudaStream_t st) {
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][ka columns], m contiguous: boxes of 64 m x 64 k
     if (!make_map(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, (unsigned long long)g.ka,
-                  (unsigned long long)(g.a_rows ? g.a_rows : g.K), (g.a_batched && !split_k) ? g.batch : 1,
+                  (unsigned long long)(g.a_rows ? g.a_rows : g.K), (g.a_batched && !split_k) ? (g.group > 1 ? g.group_items : g.batch) : 1,
                   (unsigned long long)g.lda * 2, (unsigned long long)g.a_bs * 2, 64, BK))
       return PASN_ERR_ALIGN;
   }
@@ -808,7 +822,7 @@ int launch(const Gemm& g, cudaStream_t st) {
       return PASN_ERR_ALIGN;
   } else {   // [batch][K rows][kb columns], n contiguous: boxes of 64 n x 64 k
     if (!make_map(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.B, (unsigned long long)g.kb,
-                  (unsigned long long)(g.b_rows ? g.b_rows : g.K), (g.b_batched && !split_k) ? g.batch : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
+                  (unsigned long long)(g.b_rows ? g.b_rows : g.K), (g.b_batched && !split_k) ? (g.group > 1 ? g.group_items : g.batch) : 1, (unsigned long long)g.ldb * 2, (unsigned long long)g.b_bs * 2, 64, BK))
       return PASN_ERR_ALIGN;
   }
   for (int mi = 0; mi < 2; ++mi) {

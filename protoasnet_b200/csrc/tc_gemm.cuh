@@ -62,6 +62,13 @@ struct Gemm {
   // the pooled features, so that those need not be written and read back): rowstat[(b*M + m) * 2*tiles_n + t][0..3] =
   // (sum_n v^2, sum_n v * w, sum_n w^2, 0) with w = dotvec[(m % dot_mod) * dot_ld + n] over the columns of column half-tile t
   float* rowstat; const float* dotvec; long long dot_ld; int dot_mod;
+  // optional block-diagonal batching of small per-item GEMMs (both operands MN-major and batched, one pass, K <= 64): `group` items
+  // share one 128-row tile -- item j's `group_rows` rows sit at rows [j*group_rows, +group_rows) and its K rows are the tile's
+  // j-th k-block (the other rows of that k-block's A tile are zero: the boxes are loaded at negative / out-of-range m
+  // coordinates, which the TMA unit zero-fills).  Pass M = group * group_rows, batch = ceil(group_items / group), a_bs / b_bs per
+  // ITEM; only with row statistics and no outputs.  (The per-clip pooling of few prototypes: 40 of a tile's 128 rows otherwise.)
+  int group, group_rows, group_items;
+  long long stat_rows;           // rows of rowstat that exist (0: batch * M): rows past it are not written
   int dot_early;                 // dotvec is not written by the kernel in front on the stream: it may be read before that one has completed
 };
 

@@ -72,7 +72,7 @@ Plan make_plan(const pasn_dims& d) {
   p.off_pool = take(p.w2_first ? 0 : (size_t)p.nb * d.P * 2 * d.D * 2);
   p.off_f = take(p.w2_first ? (size_t)p.nb * S * ex * d.D * 2 : 0);
   p.off_fe = take((size_t)p.nb * d.P * d.D * 4);
-  p.stat_parts = 2 * ceil_div(d.D, d.D >= 256 ? 256 : 128);
+  p.stat_parts = 2 * ceil_div(d.D, 128);   // (upper bound: 128-wide tiles; the chunk passes the count its GEMM really wrote)
   p.off_stat = take((size_t)p.nb * d.P * p.stat_parts * 16);
   p.total = o + 256;
   return p;
@@ -309,6 +309,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && (P >= 1024 || (P <= 64 && p.w2_first)))) && !occ_only &&
                           feats == nullptr && push == nullptr;
   float* STAT = reinterpret_cast<float*>(ws + p.off_stat);
+  int stat_parts = 2 * ceil_div(D, D >= 256 ? 256 : 128);   // column half-tiles of the GEMM that leaves the statistics
   const __nv_bfloat16* W13 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w13);
   const __nv_bfloat16* W4 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w4);
   const __nv_bfloat16* W5 = reinterpret_cast<const __nv_bfloat16*>(pk + L.off_w5);
@@ -440,6 +441,16 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
       if (fuse_stats) {
         g.out[0].mode = tcg::OUT_NONE;
         g.rowstat = STAT; g.dotvec = w.prototypes; g.dot_ld = D; g.dot_mod = P; g.dot_early = 1;   // (parameters: the chain does not write them)
+        // few prototypes, few voxels (image head: 40 x 49): three clips share a 128-row tile, block-diagonally -- a clip alone
+        // uses 40 of the tile's rows and two of the four epilogue row groups
+        static const int group_env = [] { const char* e = getenv("PASN_POOL_GROUP"); return e ? atoi(e) : 1; }();
+        const int G = 128 / P < 4 ? 128 / P : 4;
+        if (group_env && tok_c && ex == 1 && S <= 64 && G >= 2 && nb >= 2 * G) {
+          g.group = G; g.group_rows = P; g.group_items = nb;
+          g.M = G * P; g.batch = ceil_div(nb, G); g.bn = 128;
+          g.stat_rows = (long long)nb * P;
+          stat_parts = 2 * ceil_div(D, 128);
+        }
       }
       if ((rc = tcg::launch(g, st))) return rc;
     }
@@ -481,7 +492,7 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   }
   // ---- cosine / similarity / logits / distance / push keys (+ winner capture)
   if (fuse_stats)
-    return launch_proto_from_stats(STAT, p.stat_parts, w.last_layer, nb, P, d.K, logits + (size_t)n0 * d.K, sim + (size_t)n0 * P,
+    return launch_proto_from_stats(STAT, stat_parts, w.last_layer, nb, P, d.K, logits + (size_t)n0 * d.K, sim + (size_t)n0 * P,
                                    dist ? dist + (size_t)n0 * P : nullptr, st);
   pasn_push_args pa;
   const pasn_push_args* pp = nullptr;

@@ -36,6 +36,7 @@ class Gemm(C.Structure):     # pasn::tcg::Gemm
                 ("addin", Aux), ("signin", Aux), ("mask", Aux), ("act", C.c_int), ("out", Output * 2),
                 ("psum", C.c_void_p), ("psum_rounded", C.c_int), ("pair", C.c_int),
                 ("rowstat", C.c_void_p), ("dotvec", C.c_void_p), ("dot_ld", C.c_longlong), ("dot_mod", C.c_int),
+                ("group", C.c_int), ("group_rows", C.c_int), ("group_items", C.c_int), ("stat_rows", C.c_longlong),
                 ("dot_early", C.c_int)]
 
 
@@ -254,3 +255,29 @@ def test_row_statistics_few_rows_per_batch_item(bn):
     for t in range(2 * tiles_n):                      # each entry covers its own column half-tile
         cols = slice(half * t, half * t + half)
         _close(stat[:, :, t, 1], (ref[:, :, cols] * V.double()[None, :, cols]).sum(2), 2e-5)
+
+
+@pytest.mark.parametrize("items", [11, 148 * 3 + 5])
+def test_row_statistics_block_diagonal_groups(items):
+    """Three small per-item GEMMs (40 rows, K = 49, both operands MN-major) share one 128-row tile: item j's rows sit at
+    [40 j, 40 j + 40), its K rows are the tile's j-th k-block; the last group is ragged."""
+    P, K, N, G = 40, 49, 256, 3
+    At = _bf(_rand((items, K, P), 41))          # [item][k][m]: m contiguous
+    Bt = _bf(_rand((items, K, N), 42))          # [item][k][n]: n contiguous
+    V = _rand((P, N), 43)
+    groups = (items + G - 1) // G
+    tiles_n = N // 128
+    stat = torch.full((items * P + 64, 2 * tiles_n, 4), -1.0, device="cuda")   # + guard rows that must stay untouched
+    g = Gemm()
+    g.A, g.lda, g.a_bs, g.a_batched, g.ka, g.a_mn_major, g.a_rows = At.data_ptr(), P, K * P, 1, P, 1, K
+    g.B, g.ldb, g.b_bs, g.b_batched, g.kb, g.b_mn_major, g.b_rows = Bt.data_ptr(), N, K * N, 1, N, 1, K
+    g.M, g.N, g.K, g.batch, g.npass, g.bn = G * P, N, K, groups, 1, 128
+    g.group, g.group_rows, g.group_items, g.stat_rows = G, P, items, items * P
+    g.rowstat, g.dotvec, g.dot_ld, g.dot_mod, g.dot_early = stat.data_ptr(), V.data_ptr(), N, P, 1
+    _run(g)
+    ref = torch.bmm(At.double().transpose(1, 2), Bt.double())           # [item][P][N]
+    got = stat[:items * P].view(items, P, 2 * tiles_n, 4)
+    _close(got[..., 0].sum(2), (ref * ref).sum(2), 1e-5)
+    _close(got[..., 1].sum(2), (ref * V.double()[None]).sum(2), 2e-5)
+    _close(got[..., 2].sum(2), (V.double() ** 2).sum(1)[None].expand(items, P), 1e-5)
+    assert bool((stat[items * P:] == -1.0).all()), "rows past the last item were written"
