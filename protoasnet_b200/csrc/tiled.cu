@@ -306,7 +306,9 @@ static int tiled_chunk(const void* feat, const pasn_weights& w, const void* pack
   // Used where it pays (1, default): many prototypes (config 5: 8 MB of features per clip), and the per-clip pooling GEMM of
   // few prototypes straight into features (image head: the GEMM keeps the prototype slices in shared memory).  Elsewhere the
   // statistics' vector reads (a row per lane) cost the epilogue more than the round trip.  2: always, 0: never.
-  const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && (P >= 1024 || (P <= 64 && p.w2_first)))) && !occ_only &&
+  // (Both are W2-before-pooling shapes: the statistics ride in the per-clip pooling GEMM.  The other order's last GEMM can
+  // leave them too -- PASN_TILED_STATS=2 -- but no named config takes that way, so it is not on by default.)
+  const bool fuse_stats = (stats_env == 2 || (stats_env == 1 && p.w2_first && (P >= 1024 || P <= 64))) && !occ_only &&
                           feats == nullptr && push == nullptr;
   float* STAT = reinterpret_cast<float*>(ws + p.off_stat);
   int stat_parts = 2 * ceil_div(D, D >= 256 ? 256 : 128);   // column half-tiles of the GEMM that leaves the statistics

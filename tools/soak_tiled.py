@@ -17,10 +17,14 @@ for cfg, n, dt in (("cfg2_image", 300, torch.bfloat16), ("cfg2_image", 37, torch
     for xx, name in ((x, "ncs"), (x.contiguous(memory_format=torch.channels_last_3d if dims.ndim == 3 else torch.channels_last), "nsc")):
         with torch.no_grad():
             ref = m.push_forward(xx)
+            reff = m(xx)      # plain forward: row statistics instead of stored features where the path uses them
             for i in range(40):
                 out = m.push_forward(xx)
-                if not all(torch.equal(a, b) for a, b in zip(out, ref)):
+                outf = m(xx)
+                if not all(torch.equal(a, b) for a, b in zip(out, ref)) or not all(torch.equal(a, b) for a, b in zip(outf, reff)):
                     bad += 1; print("FORWARD MISMATCH", cfg, n, name, i); break
+            if float((reff[1] - (1 - ref[1])).abs().max()) > 2e-6 * (1 if dt == torch.float32 else 50):
+                bad += 1; print("forward / push_forward similarity differ", cfg, n, name, float((reff[1] - (1 - ref[1])).abs().max()))
         print(cfg, n, dt, name, "forward ok", f"{time.time() - t0:.0f}s", flush=True)
     if cfg == "cfg5_scaled":
         continue
