@@ -30,6 +30,13 @@ def test_library_exports_every_declared_symbol():
     assert b"workspace" in lib.pasn_strerror(-2)
 
 
+def test_gemm_descriptor_mirror_matches_the_library():
+    """The ctypes mirror of pasn::tcg::Gemm used by the GEMM unit tests and tools/probe_chain_gemms.py has the library's size
+    (a field added on one side only would shift every later field silently)."""
+    from tests.test_tc_gemm_gpu import Gemm
+    assert _lib.load().pasn_debug_tc_gemm_desc_bytes() == C.sizeof(Gemm)
+
+
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     bad = _lib.PasnDims(1, 8, 7, 4, 2, 9, 0, 0, 0, 0)          # odd D
